@@ -1,0 +1,604 @@
+/*
+ * aad_gpu.c -- host side of libaad_b200.so, in C: device context, scratch memory, and the
+ * pipelines that move streams host -> device -> host around the kernels in aad_kernels.cu.
+ *
+ * Pipelining: the whole batch stays resident on the device (12,500 ten-second clips are
+ * ~14 GB of the 180 GB HBM); the COPIES are sliced by block range.  Slice k's H2D runs on
+ * one stream while slice k-1's kernel runs on a second and slice k-2's D2H on a third.  The
+ * encoder's chain state crosses slices through a device-resident state array, exactly the way
+ * the reference carries its per-channel processor from block to block
+ * (src/aad_encoder.c:21,853-886) -- so slicing never changes a byte of output.
+ */
+#define _GNU_SOURCE
+#include "aad_gpu_internal.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static __thread char tl_error[320] = "";
+static uint32_t g_max_channels = AADF_MAX_CHANNELS;
+
+void aadgpu_set_error(const char *msg) { snprintf(tl_error, sizeof(tl_error), "%s", msg ? msg : ""); }
+
+AADApiResult aadgpu_fail(const char *what, cudaError_t err)
+{
+  snprintf(tl_error, sizeof(tl_error), "%s: %s", what, cudaGetErrorString(err));
+  return AAD_APIRESULT_NG;
+}
+
+const char *AADGpu_LastError(void) { return tl_error; }
+uint64_t AADGpu_KernelLaunchCount(void) { return aadk_launch_count(); }
+uint32_t aadgpu_max_channels(void) { return g_max_channels; }
+uint32_t AADGpu_GetMaxChannels(void) { return g_max_channels; }
+void AADGpu_SetMaxChannels(uint32_t n)
+{
+  if (n >= 1 && n <= AADF_MAX_CHANNELS) g_max_channels = n;
+}
+
+#define CU(call, what)                                  \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return aadgpu_fail(what, e__); \
+  } while (0)
+
+int AADGpu_DeviceCount(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+struct AADGpu *AADGpu_Create(int device)
+{
+  if (device < 0 || device >= AADGpu_DeviceCount()) {
+    aadgpu_set_error("AADGpu_Create: no such CUDA device (this library has no CPU fallback)");
+    return NULL;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    aadgpu_fail("cudaSetDevice", cudaGetLastError());
+    return NULL;
+  }
+  struct AADGpu *g = (struct AADGpu *)calloc(1, sizeof(*g));
+  if (!g) return NULL;
+  g->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_run, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking);
+  for (int i = 0; i < 16 && e == cudaSuccess; i++) {
+    e = cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_run[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    aadgpu_fail("AADGpu_Create", e);
+    AADGpu_Destroy(g);
+    return NULL;
+  }
+  return g;
+}
+
+void AADGpu_Destroy(struct AADGpu *g)
+{
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut };
+  for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
+    if (bufs[i]->ptr) cudaFree(bufs[i]->ptr);
+  for (int i = 0; i < 16; i++) {
+    if (g->ev_in[i]) cudaEventDestroy(g->ev_in[i]);
+    if (g->ev_run[i]) cudaEventDestroy(g->ev_run[i]);
+  }
+  if (g->s_in) cudaStreamDestroy(g->s_in);
+  if (g->s_run) cudaStreamDestroy(g->s_run);
+  if (g->s_out) cudaStreamDestroy(g->s_out);
+  free(g);
+}
+
+static pthread_mutex_t g_default_lock = PTHREAD_MUTEX_INITIALIZER;
+static struct AADGpu *g_default = NULL;
+
+struct AADGpu *aadgpu_default(void)
+{
+  pthread_mutex_lock(&g_default_lock);
+  if (!g_default) {
+    const char *env = getenv("AAD_B200_DEVICE");
+    g_default = AADGpu_Create(env ? atoi(env) : 0);
+  }
+  struct AADGpu *g = g_default;
+  pthread_mutex_unlock(&g_default_lock);
+  return g;
+}
+
+void *AADGpu_HostAlloc(size_t bytes)
+{
+  void *p = NULL;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    aadgpu_fail("cudaMallocHost", cudaGetLastError());
+    return NULL;
+  }
+  return p;
+}
+
+void AADGpu_HostFree(void *p)
+{
+  if (p) cudaFreeHost(p);
+}
+
+int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes)
+{
+  (void)gpu;
+  if (b->cap >= bytes && b->ptr) return 1;
+  if (b->ptr) cudaFree(b->ptr);
+  b->ptr = NULL;
+  b->cap = 0;
+  const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+  if (cudaMalloc(&b->ptr, want) != cudaSuccess) {
+    aadgpu_fail("cudaMalloc", cudaGetLastError());
+    b->ptr = NULL;
+    return 0;
+  }
+  b->cap = want;
+  return 1;
+}
+
+/* ---- parameter checks ------------------------------------------------------------------- */
+
+/* The checks AADEncoder_SetEncodeParameter (src/aad_encoder.c:741-770) and
+ * AADEncoder_EncodeHeader (src/aad_encoder.c:149-185) apply, in that order. */
+static AADApiResult check_encode_shape(const struct AADEncodeParameter *prm, uint32_t num_samples,
+                                       struct aadf_geometry *geo)
+{
+  uint32_t bs = 0, spb = 0;
+  if (prm->bits_per_sample == 0 || prm->bits_per_sample > AAD_MAX_BITS_PER_SAMPLE) return AAD_APIRESULT_INVALID_FORMAT;
+  if (prm->max_block_size < AADF_CHANNEL_HEADER_BYTES * (uint32_t)prm->num_channels) return AAD_APIRESULT_INVALID_FORMAT;
+  if ((uint32_t)prm->ch_process_method >= (uint32_t)AAD_CH_PROCESS_METHOD_INVALID) return AAD_APIRESULT_INVALID_FORMAT;
+  if (!aadf_block_geometry(prm->max_block_size, prm->num_channels, prm->bits_per_sample, g_max_channels, &bs, &spb))
+    return AAD_APIRESULT_INVALID_FORMAT;
+  if (num_samples == 0 || prm->sampling_rate == 0) return AAD_APIRESULT_INVALID_FORMAT;
+  if (prm->bits_per_sample < AAD_MIN_BITS_PER_SAMPLE) return AAD_APIRESULT_INVALID_FORMAT;
+  if (bs <= AADF_CHANNEL_HEADER_BYTES * (uint32_t)prm->num_channels) return AAD_APIRESULT_INVALID_FORMAT;
+  if (prm->ch_process_method == AAD_CH_PROCESS_METHOD_MS && prm->num_channels == 1) return AAD_APIRESULT_INVALID_FORMAT;
+  geo->channels = prm->num_channels;
+  geo->bits = prm->bits_per_sample;
+  geo->block_size = bs;
+  geo->samples_per_block = spb;
+  geo->ms = (prm->ch_process_method == AAD_CH_PROCESS_METHOD_MS) ? 1u : 0u;
+  return AAD_APIRESULT_OK;
+}
+
+uint64_t AADGpu_StreamBytesBound(const struct AADEncodeParameter *prm, uint32_t num_samples)
+{
+  struct aadf_geometry geo;
+  if (!prm || check_encode_shape(prm, num_samples ? num_samples : 1, &geo) != AAD_APIRESULT_OK) return 0;
+  return aadf_stream_bytes_bound(num_samples, geo.block_size, geo.samples_per_block);
+}
+
+uint64_t AADGpu_StreamBytes(const struct AADEncodeParameter *prm, uint32_t num_samples)
+{
+  struct aadf_geometry geo;
+  if (!prm || check_encode_shape(prm, num_samples ? num_samples : 1, &geo) != AAD_APIRESULT_OK) return 0;
+  return aadf_stream_bytes(num_samples, geo.channels, geo.bits, geo.block_size, geo.samples_per_block);
+}
+
+static AADApiResult check_batch(const struct AADGpuBatch *b, struct aadf_geometry *geo)
+{
+  const AADApiResult r = check_encode_shape(&b->param, b->num_samples, geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (b->pcm_channel_stride < b->num_samples) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  if (b->pcm_stream_stride < b->pcm_channel_stride * (geo->channels - 1) + b->num_samples)
+    return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  if (b->aad_stream_stride < aadf_stream_bytes_bound(b->num_samples, geo->block_size, geo->samples_per_block))
+    return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  if (b->aad_stream_stride > 0xFFFFFFFFull) return AAD_APIRESULT_INVALID_ARGUMENT;
+  return AAD_APIRESULT_OK;
+}
+
+/* ---- device-resident entry points -------------------------------------------------------- */
+
+AADApiResult AADGpu_EncodeBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm_dev,
+                                      const uint32_t *num_samples_dev, uint8_t *aad_dev, uint32_t *out_sizes_dev,
+                                      void *stream)
+{
+  if (!gpu || !batch || !pcm_dev || !aad_dev) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_batch(batch, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (batch->num_streams == 0) return AAD_APIRESULT_OK;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  struct aadk_encode_params p;
+  memset(&p, 0, sizeof(p));
+  p.pcm = pcm_dev;
+  p.pcm_clip_stride = batch->pcm_stream_stride;
+  p.pcm_ch_stride = batch->pcm_channel_stride;
+  p.num_samples = num_samples_dev;
+  p.uniform_samples = batch->num_samples;
+  p.num_streams = batch->num_streams;
+  p.geo = geo;
+  p.sampling_rate = batch->param.sampling_rate;
+  p.trials = batch->param.num_encode_trials;
+  p.aad = aad_dev;
+  p.aad_stride = batch->aad_stream_stride;
+  p.out_sizes = out_sizes_dev;
+  p.block_begin = 0;
+  p.block_end = aadf_num_blocks(batch->num_samples, geo.samples_per_block);
+  CU((cudaError_t)aadk_launch_encode(&p, stream), "encode kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_DecodeBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad_dev,
+                                      const uint32_t *sizes_dev, int16_t *pcm_dev, void *stream)
+{
+  if (!gpu || !batch || !pcm_dev || !aad_dev) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_batch(batch, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (batch->num_streams == 0) return AAD_APIRESULT_OK;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  struct aadk_decode_params p;
+  memset(&p, 0, sizeof(p));
+  p.aad = aad_dev;
+  p.aad_stride = batch->aad_stream_stride;
+  p.sizes = sizes_dev;
+  p.uniform_size = (uint32_t)batch->aad_stream_stride;
+  p.num_streams = batch->num_streams;
+  p.geo = geo;
+  p.block_begin = 0;
+  p.block_end = aadf_num_blocks(batch->num_samples, geo.samples_per_block);
+  p.read_headers = 1;
+  p.pcm = pcm_dev;
+  p.pcm_clip_stride = batch->pcm_stream_stride;
+  p.pcm_ch_stride = batch->pcm_channel_stride;
+  CU((cudaError_t)aadk_launch_decode(&p, stream), "decode kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+/* ---- sine table for the synthetic generator ---------------------------------------------- */
+
+void AADGpu_SynthLut(int16_t lut[1024]);
+void AADGpu_SynthLut(int16_t lut[1024])
+{
+  for (int k = 0; k < 1024; k++) lut[k] = (int16_t)lrint(32767.0 * sin(2.0 * 3.14159265358979323846 * k / 1024.0));
+}
+
+AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch, uint32_t first_stream,
+                                     int16_t *pcm_dev, void *stream)
+{
+  if (!gpu || !batch || !pcm_dev) return AAD_APIRESULT_INVALID_ARGUMENT;
+  if (batch->param.num_channels == 0 || batch->param.sampling_rate == 0) return AAD_APIRESULT_INVALID_FORMAT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  if (!gpu->lut_ready) {
+    int16_t lut[1024];
+    AADGpu_SynthLut(lut);
+    if (!aadgpu_reserve(gpu, &gpu->lut, sizeof(lut))) return AAD_APIRESULT_NG;
+    CU(cudaMemcpy(gpu->lut.ptr, lut, sizeof(lut), cudaMemcpyHostToDevice), "upload sine table");
+    gpu->lut_ready = 1;
+  }
+  struct aadk_synth_params p;
+  memset(&p, 0, sizeof(p));
+  p.pcm = pcm_dev;
+  p.pcm_clip_stride = batch->pcm_stream_stride;
+  p.pcm_ch_stride = batch->pcm_channel_stride;
+  p.num_streams = batch->num_streams;
+  p.channels = batch->param.num_channels;
+  p.num_samples = batch->num_samples;
+  p.sampling_rate = batch->param.sampling_rate;
+  p.first_stream = first_stream;
+  p.lut = (const int16_t *)gpu->lut.ptr;
+  CU((cudaError_t)aadk_launch_synth(&p, stream), "synth kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_Deinterleave16Device(struct AADGpu *gpu, const int16_t *interleaved_dev, int16_t *planar_dev,
+                                         uint64_t channel_stride, uint32_t channels, uint32_t num_samples,
+                                         void *stream)
+{
+  if (!gpu || !interleaved_dev || !planar_dev) return AAD_APIRESULT_INVALID_ARGUMENT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  CU((cudaError_t)aadk_launch_deinterleave16(interleaved_dev, planar_dev, channel_stride, channels, num_samples, stream),
+     "deinterleave kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_Interleave16Device(struct AADGpu *gpu, const int16_t *planar_dev, uint64_t channel_stride,
+                                       int16_t *interleaved_dev, uint32_t channels, uint32_t num_samples, void *stream)
+{
+  if (!gpu || !interleaved_dev || !planar_dev) return AAD_APIRESULT_INVALID_ARGUMENT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  CU((cudaError_t)aadk_launch_interleave16(planar_dev, channel_stride, interleaved_dev, channels, num_samples, stream),
+     "interleave kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+/* ---- host pipelines ----------------------------------------------------------------------- */
+
+static uint64_t round_up64(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+/* how many block-range slices to cut the copies into: ~32 MiB of PCM each, at most 16 */
+static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
+{
+  uint64_t s = pcm_bytes / ((uint64_t)32 << 20);
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  if (s > num_blocks) s = num_blocks ? num_blocks : 1;
+  return (uint32_t)s;
+}
+
+/* 2-D copy of `rows` rows of `width` bytes; collapses to one 1-D copy when both sides are dense */
+static cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                             enum cudaMemcpyKind kind, cudaStream_t s)
+{
+  if (rows == 0 || width == 0) return cudaSuccess;
+  if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, s);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s);
+}
+
+/* rows of a batch's PCM: uniform pitch when streams are packed back to back */
+static cudaError_t copy_pcm_slice(const struct AADGpuBatch *b, uint32_t C, int to_device, int16_t *dev, uint64_t dev_pitch,
+                                  int16_t *host, uint32_t s0, uint32_t s1, cudaStream_t st)
+{
+  const size_t width = (size_t)(s1 - s0) * sizeof(int16_t);
+  const enum cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  if (b->pcm_stream_stride == b->pcm_channel_stride * C) {
+    void *d = dev + s0;
+    void *h = host + s0;
+    return to_device ? copy_rows(d, dev_pitch * 2, h, b->pcm_channel_stride * 2, width, (size_t)b->num_streams * C, kind, st)
+                     : copy_rows(h, b->pcm_channel_stride * 2, d, dev_pitch * 2, width, (size_t)b->num_streams * C, kind, st);
+  }
+  for (uint32_t i = 0; i < b->num_streams; i++) {
+    void *d = dev + (uint64_t)i * C * dev_pitch + s0;
+    void *h = host + (uint64_t)i * b->pcm_stream_stride + s0;
+    const cudaError_t e = to_device ? copy_rows(d, dev_pitch * 2, h, b->pcm_channel_stride * 2, width, C, kind, st)
+                                    : copy_rows(h, b->pcm_channel_stride * 2, d, dev_pitch * 2, width, C, kind, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
+                                const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes)
+{
+  if (!gpu || !batch || !pcm || !aad) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_batch(batch, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  const uint32_t N = batch->num_streams, C = geo.channels, ns = batch->num_samples;
+  if (N == 0) return AAD_APIRESULT_OK;
+  if (num_samples)
+    for (uint32_t i = 0; i < N; i++)
+      if (num_samples[i] == 0 || num_samples[i] > ns) return AAD_APIRESULT_INVALID_FORMAT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+
+  const uint32_t spb = geo.samples_per_block, bs = geo.block_size;
+  const uint32_t nblk = aadf_num_blocks(ns, spb);
+  const uint64_t pitch = round_up64(ns, 64);                              /* samples, 128-byte rows */
+  const uint64_t astride = round_up64(aadf_stream_bytes_bound(ns, bs, spb) + 1, 128);
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)N * astride + 128)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->state, (size_t)N * C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
+  if (num_samples && !aadgpu_reserve(gpu, &gpu->lens, (size_t)N * 4)) return AAD_APIRESULT_NG;
+  int16_t *d_pcm = (int16_t *)gpu->pcm.ptr;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;   /* block 0 of every stream lands 32-byte aligned */
+
+  CU(cudaMemsetAsync(gpu->state.ptr, 0, (size_t)N * C * AADK_STATE_WORDS * 4, gpu->s_run), "memset state");
+  CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)N * astride + 128, gpu->s_run), "memset aad");
+  if (num_samples)
+    CU(cudaMemcpyAsync(gpu->lens.ptr, num_samples, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D lengths");
+
+  struct aadk_encode_params p;
+  memset(&p, 0, sizeof(p));
+  p.pcm = d_pcm;
+  p.pcm_clip_stride = (uint64_t)C * pitch;
+  p.pcm_ch_stride = pitch;
+  p.num_samples = num_samples ? (const uint32_t *)gpu->lens.ptr : NULL;
+  p.uniform_samples = ns;
+  p.num_streams = N;
+  p.geo = geo;
+  p.sampling_rate = batch->param.sampling_rate;
+  p.trials = batch->param.num_encode_trials;
+  p.aad = d_aad;
+  p.aad_stride = astride;
+  p.state_in = (const int32_t *)gpu->state.ptr;
+  p.state_out = (int32_t *)gpu->state.ptr;
+
+  const uint32_t slices = pick_slices((uint64_t)N * C * ns * 2, nblk);
+  for (uint32_t k = 0; k < slices; k++) {
+    const uint32_t b0 = (uint32_t)((uint64_t)nblk * k / slices), b1 = (uint32_t)((uint64_t)nblk * (k + 1) / slices);
+    const uint32_t s0 = b0 * spb, s1 = (b1 * (uint64_t)spb < ns) ? b1 * spb : ns;
+    CU(copy_pcm_slice(batch, C, 1, d_pcm, pitch, (int16_t *)pcm, s0, s1, gpu->s_in), "H2D pcm");
+    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
+    p.block_begin = b0;
+    p.block_end = b1;
+    CU((cudaError_t)aadk_launch_encode(&p, gpu->s_run), "encode kernel launch");
+    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
+    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+    const size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+    CU(copy_rows(aad + off, batch->aad_stream_stride, d_aad + off, astride, end - off, N, cudaMemcpyDeviceToHost,
+                 gpu->s_out), "D2H aad");
+  }
+  CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  if (out_sizes)
+    for (uint32_t i = 0; i < N; i++)
+      out_sizes[i] = (uint32_t)aadf_stream_bytes(num_samples ? num_samples[i] : ns, C, geo.bits, bs, spb);
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad,
+                                const uint32_t *sizes, int16_t *pcm)
+{
+  if (!gpu || !batch || !pcm || !aad) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_batch(batch, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  const uint32_t N = batch->num_streams, C = geo.channels, ns = batch->num_samples;
+  if (N == 0) return AAD_APIRESULT_OK;
+  /* every stream must carry the geometry the batch describes (one kernel configuration) */
+  for (uint32_t i = 0; i < N; i++) {
+    const uint8_t *h = aad + (uint64_t)i * batch->aad_stream_stride;
+    const uint32_t sz = sizes ? sizes[i] : (uint32_t)batch->aad_stream_stride;
+    if (sz < AADF_FILE_HEADER_BYTES) return AAD_APIRESULT_INSUFFICIENT_DATA;
+    if (h[0] != 'A' || h[1] != 'A' || h[2] != 'D' || h[3] != 0) return AAD_APIRESULT_INVALID_FORMAT;
+    if (aadf_get_be32(h + 4) != AAD_FORMAT_VERSION || aadf_get_be32(h + 8) != AAD_CODEC_VERSION ||
+        aadf_get_be16(h + 12) != C || aadf_get_be16(h + 22) != geo.bits || aadf_get_be16(h + 24) != geo.block_size ||
+        aadf_get_be32(h + 26) != geo.samples_per_block || h[30] != geo.ms)
+      return AAD_APIRESULT_INVALID_FORMAT;
+    const uint32_t n = aadf_get_be32(h + 14);
+    if (n == 0 || aadf_get_be32(h + 18) == 0) return AAD_APIRESULT_INVALID_FORMAT;
+    if (n > ns) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  }
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+
+  const uint32_t spb = geo.samples_per_block, bs = geo.block_size;
+  const uint32_t nblk = aadf_num_blocks(ns, spb);
+  const uint64_t pitch = round_up64(ns, 64);
+  const uint64_t bound = aadf_stream_bytes_bound(ns, bs, spb);
+  const uint64_t astride = round_up64(bound + 1, 128);
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)N * astride + 128)) return AAD_APIRESULT_NG;
+  if (sizes && !aadgpu_reserve(gpu, &gpu->sizes, (size_t)N * 4)) return AAD_APIRESULT_NG;
+  int16_t *d_pcm = (int16_t *)gpu->pcm.ptr;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
+  if (sizes) CU(cudaMemcpyAsync(gpu->sizes.ptr, sizes, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_in), "H2D sizes");
+
+  struct aadk_decode_params p;
+  memset(&p, 0, sizeof(p));
+  p.aad = d_aad;
+  p.aad_stride = astride;
+  p.sizes = sizes ? (const uint32_t *)gpu->sizes.ptr : NULL;
+  p.uniform_size = (uint32_t)(batch->aad_stream_stride < bound ? batch->aad_stream_stride : bound);
+  p.num_streams = N;
+  p.geo = geo;
+  p.read_headers = 1;
+  p.pcm = d_pcm;
+  p.pcm_clip_stride = (uint64_t)C * pitch;
+  p.pcm_ch_stride = pitch;
+
+  const uint32_t slices = pick_slices((uint64_t)N * C * ns * 2, nblk);
+  for (uint32_t k = 0; k < slices; k++) {
+    const uint32_t b0 = (uint32_t)((uint64_t)nblk * k / slices), b1 = (uint32_t)((uint64_t)nblk * (k + 1) / slices);
+    const uint32_t s0 = b0 * spb, s1 = (b1 * (uint64_t)spb < ns) ? b1 * spb : ns;
+    const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+    size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+    if (end > batch->aad_stream_stride) end = batch->aad_stream_stride;
+    CU(copy_rows(d_aad + off, astride, aad + off, batch->aad_stream_stride, end - off, N, cudaMemcpyHostToDevice,
+                 gpu->s_in), "H2D aad");
+    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
+    p.block_begin = b0;
+    p.block_end = b1;
+    CU((cudaError_t)aadk_launch_decode(&p, gpu->s_run), "decode kernel launch");
+    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
+    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    CU(copy_pcm_slice(batch, C, 0, d_pcm, pitch, pcm, s0, s1, gpu->s_out), "D2H pcm");
+  }
+  CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  return AAD_APIRESULT_OK;
+}
+
+/* ---- single-stream paths behind the drop-in API ------------------------------------------- */
+
+AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, uint32_t sampling_rate,
+                                      uint32_t trials, const int32_t *const *input, uint32_t num_samples,
+                                      int32_t *state, uint8_t *data, uint32_t *output_size)
+{
+  const uint32_t C = geo->channels;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  const uint64_t pitch = round_up64(num_samples, 64);
+  const uint64_t bytes = aadf_stream_bytes(num_samples, C, geo->bits, geo->block_size, geo->samples_per_block);
+  const uint64_t bound = aadf_stream_bytes_bound(num_samples, geo->block_size, geo->samples_per_block);
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->state, (size_t)C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
+  int32_t *d_pcm = (int32_t *)gpu->pcm.ptr;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
+  cudaStream_t s = gpu->s_run;
+  for (uint32_t c = 0; c < C; c++)
+    CU(cudaMemcpyAsync(d_pcm + c * pitch, input[c], (size_t)num_samples * 4, cudaMemcpyHostToDevice, s), "H2D pcm");
+  CU(cudaMemcpyAsync(gpu->state.ptr, state, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyHostToDevice, s), "H2D state");
+  struct aadk_encode_params p;
+  memset(&p, 0, sizeof(p));
+  p.pcm = d_pcm;
+  p.pcm_clip_stride = (uint64_t)C * pitch;
+  p.pcm_ch_stride = pitch;
+  p.in32 = 1;
+  p.uniform_samples = num_samples;
+  p.num_streams = 1;
+  p.geo = *geo;
+  p.sampling_rate = sampling_rate;
+  p.trials = trials;
+  p.aad = d_aad;
+  p.aad_stride = bound;
+  p.state_in = (const int32_t *)gpu->state.ptr;
+  p.state_out = (int32_t *)gpu->state.ptr;
+  p.block_begin = 0;
+  p.block_end = aadf_num_blocks(num_samples, geo->samples_per_block);
+  CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
+  CU(cudaMemcpyAsync(data, d_aad, (size_t)bytes, cudaMemcpyDeviceToHost, s), "D2H aad");
+  CU(cudaMemcpyAsync(state, gpu->state.ptr, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyDeviceToHost, s), "D2H state");
+  CU(cudaStreamSynchronize(s), "sync");
+  *output_size = (uint32_t)bytes;
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *data,
+                                      uint32_t data_size, uint32_t num_blocks, uint32_t num_samples,
+                                      uint32_t buf_samples, int32_t *const *buffer)
+{
+  const uint32_t C = geo->channels, spb = geo->samples_per_block, bs = geo->block_size;
+  if (num_blocks == 0) return AAD_APIRESULT_OK;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  /* samples the block loop writes: every block min(spb, room) -- src/aad_decoder.c:356,524 */
+  uint64_t total = (uint64_t)num_blocks * spb;
+  if (total > buf_samples) total = buf_samples;
+  const uint64_t pitch = round_up64(total, 64);
+  uint64_t span = AADF_FILE_HEADER_BYTES + (uint64_t)num_blocks * bs;
+  if (span > data_size) span = data_size;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 128)) return AAD_APIRESULT_NG;
+  int32_t *d_pcm = (int32_t *)gpu->pcm.ptr;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
+
+  struct aadk_decode_params p;
+  memset(&p, 0, sizeof(p));
+  p.aad = d_aad;
+  p.aad_stride = span;
+  p.uniform_size = (uint32_t)span;
+  p.num_streams = 1;
+  p.geo = *geo;
+  p.uniform_samples = num_samples;
+  p.buf_samples = buf_samples;
+  p.pcm = d_pcm;
+  p.pcm_clip_stride = (uint64_t)C * pitch;
+  p.pcm_ch_stride = pitch;
+  p.out32 = 1;
+
+  const uint32_t slices = pick_slices(total * C * 4, num_blocks);
+  for (uint32_t k = 0; k < slices; k++) {
+    const uint32_t b0 = (uint32_t)((uint64_t)num_blocks * k / slices);
+    const uint32_t b1 = (uint32_t)((uint64_t)num_blocks * (k + 1) / slices);
+    const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < total) ? (uint64_t)b1 * spb : total;
+    const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+    size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+    if (end > span) end = span;
+    CU(cudaMemcpyAsync(d_aad + off, data + off, end - off, cudaMemcpyHostToDevice, gpu->s_in), "H2D aad");
+    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
+    p.block_begin = b0;
+    p.block_end = b1;
+    CU((cudaError_t)aadk_launch_decode(&p, gpu->s_run), "decode kernel launch");
+    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
+    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    for (uint32_t c = 0; c < C && s1 > s0; c++)
+      CU(cudaMemcpyAsync(buffer[c] + s0, d_pcm + c * pitch + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost,
+                         gpu->s_out), "D2H pcm");
+  }
+  CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  return AAD_APIRESULT_OK;
+}

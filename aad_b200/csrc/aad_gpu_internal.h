@@ -1,0 +1,55 @@
+/*
+ * aad_gpu_internal.h -- private to the host C sources of libaad_b200.so.
+ */
+#ifndef AAD_GPU_INTERNAL_H
+#define AAD_GPU_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime_api.h>
+
+#include "aad_b200.h"
+#include "aad_format.h"
+#include "aad_kernels.h"
+
+#define AADGPU_PIPE_STREAMS 3   /* H2D, kernels, D2H */
+
+struct aadgpu_buffer {
+  void *ptr;
+  size_t cap;
+};
+
+struct AADGpu {
+  int device;
+  cudaStream_t s_in, s_run, s_out;
+  cudaEvent_t ev_in[16], ev_run[16];
+  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut;
+  int lut_ready;
+};
+
+/* error plumbing: records a message for AADGpu_LastError() and returns AAD_APIRESULT_NG */
+AADApiResult aadgpu_fail(const char *what, cudaError_t err);
+void aadgpu_set_error(const char *msg);
+
+/* grow-only device scratch */
+int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes);
+
+/* process-wide default context used by the drop-in handles (created on first use on the
+ * device named by $AAD_B200_DEVICE, default 0); NULL when CUDA is unusable */
+struct AADGpu *aadgpu_default(void);
+
+uint32_t aadgpu_max_channels(void);
+
+/* Single-stream paths behind AADEncoder_EncodeWhole / AADDecoder_DecodeWhole / _DecodeBlock.
+ * Host pointers, int32 PCM (the reference API type). */
+AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, uint32_t sampling_rate,
+                                      uint32_t trials, const int32_t *const *input, uint32_t num_samples,
+                                      int32_t *state /* [channels][AADK_STATE_WORDS] in/out */, uint8_t *data,
+                                      uint32_t *output_size);
+/* Decodes blocks [0, num_blocks) found at data + 31 (data_size counts from data[0]);
+ * num_samples / buf_samples as in src/aad_decoder.c:478-538. */
+AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *data,
+                                      uint32_t data_size, uint32_t num_blocks, uint32_t num_samples,
+                                      uint32_t buf_samples, int32_t *const *buffer);
+
+#endif

@@ -1,0 +1,512 @@
+/*
+ * aad_kernels.cu -- sm_100a kernels for the AAD ADPCM hot path.
+ *
+ * Work decomposition:
+ *   decode : one thread per (stream, block, channel) chain -- every block header reloads the
+ *            full predictor / step state (src/aad_decoder.c:364-380), so chains are independent.
+ *   encode : one thread per (stream, channel) chain walking its blocks in order -- the encoder
+ *            carries weight[4] and stepsize_index from block to block
+ *            (src/aad_encoder.c:21,853-886), so a stream is serial; parallelism is across streams.
+ *
+ * All sample arithmetic is 32-bit wrapping (unsigned multiply/add, arithmetic >> on int32),
+ * matching what the reference compiles to.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aad_format.h"
+#include "aad_kernels.h"
+#include "aad_tables_data.h"
+
+namespace {
+
+__device__ const uint16_t g_step_table[256] = AADK_STEP_TABLE_INIT;
+__device__ const int16_t g_delta2[2] = AADK_DELTA2_INIT;
+__device__ const int16_t g_delta3[4] = AADK_DELTA3_INIT;
+__device__ const int16_t g_delta4[8] = AADK_DELTA4_INIT;
+
+unsigned long long g_launches = 0;
+
+__device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+__device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+__device__ __forceinline__ int32_t clamp16(int32_t v) { return max(-32768, min(32767, v)); }
+
+/* Tables staged in shared memory: the step lookup is lane-divergent, which would serialise
+ * on the constant cache. */
+struct SharedTables {
+  uint16_t step[256];
+  int16_t delta[8];
+};
+
+template <int BITS>
+__device__ __forceinline__ void load_tables(SharedTables &t)
+{
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t.step[i] = g_step_table[i];
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x;
+    int16_t d = 0;
+    if (BITS == 4) d = g_delta4[k];
+    if (BITS == 3) d = g_delta3[k & 3];
+    if (BITS == 2) d = g_delta2[k & 1];
+    t.delta[k] = d;
+  }
+  __syncthreads();
+}
+
+/* One adaptive chain: history h[0] newest, Q15 weights, Q4 step index. */
+struct Chain {
+  int32_t h[4];
+  int32_t w[4];
+  int32_t idx;
+};
+
+__device__ __forceinline__ int32_t chain_predict(const Chain &c)
+{
+  int32_t acc = 1 << 14;
+#pragma unroll
+  for (int k = 0; k < 4; k++) acc = wadd(acc, wmul(c.h[k], c.w[k]));
+  return acc >> 15;
+}
+
+/* Dequantise `code`, reconstruct, adapt (src/aad_encoder.c:378-406, src/aad_decoder.c:283-315).
+ * Returns the reconstructed sample; qdiff receives the signed dequantised difference. */
+template <int BITS>
+__device__ __forceinline__ int32_t chain_absorb(Chain &c, uint32_t code, int32_t predict, int32_t step,
+                                                const SharedTables &t, int32_t &qdiff)
+{
+  constexpr uint32_t kSign = 1u << (BITS - 1);
+  const uint32_t mag = code & (kSign - 1u);
+  int32_t q = (step * (int32_t)(2u * mag + 1u)) >> (BITS - 1);
+  q = (code & kSign) ? -q : q;
+  qdiff = q;
+  const int32_t idx = (int32_t)(int16_t)(c.idx + t.delta[mag]);
+  c.idx = max(0, min(AADF_INDEX_MAX, idx));
+  const int32_t recon = clamp16(wadd(q, predict));
+#pragma unroll
+  for (int k = 0; k < 4; k++) c.w[k] = wadd(c.w[k], wadd(wmul(q, c.h[k]), 1 << 14) >> 18);
+  c.h[3] = c.h[2];
+  c.h[2] = c.h[1];
+  c.h[1] = c.h[0];
+  c.h[0] = recon;
+  return recon;
+}
+
+template <int BITS>
+__device__ __forceinline__ int32_t chain_decode(Chain &c, uint32_t code, const SharedTables &t)
+{
+  const int32_t step = t.step[(c.idx + 8) >> 4];
+  const int32_t predict = chain_predict(c);
+  int32_t q;
+  return chain_absorb<BITS>(c, code, predict, step, t, q);
+}
+
+/* src/aad_encoder.c:343-410 */
+template <int BITS>
+__device__ __forceinline__ uint32_t chain_encode(Chain &c, int32_t sample, const SharedTables &t, int32_t &qdiff)
+{
+  constexpr uint32_t kSign = 1u << (BITS - 1);
+  const int32_t step = t.step[(c.idx + 8) >> 4];
+  const int32_t predict = chain_predict(c);
+  const int32_t diff = wsub(sample, predict);
+  const bool neg = diff < 0;
+  const uint32_t mag_in = (uint32_t)(neg ? wsub(0, diff) : diff) << (BITS - 2);
+  /* both operands are non-negative and < 2^31: unsigned divide == the reference's signed one */
+  uint32_t q = mag_in / (uint32_t)step;
+  q = min(q, kSign - 1u);
+  const uint32_t code = q | (neg ? kSign : 0u);
+  chain_absorb<BITS>(c, code, predict, step, t, qdiff);
+  return code;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * decode, generic path: any channel count / alignment / ragged tail.
+ * ------------------------------------------------------------------------------------------ */
+template <int BITS>
+__global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_params p)
+{
+  __shared__ SharedTables tab;
+  load_tables<BITS>(tab);
+
+  constexpr uint32_t GS = (BITS == 4) ? 2 : (BITS == 3 ? 8 : 4);   /* samples per group */
+  constexpr uint32_t GB = (BITS == 3) ? 3 : 1;                     /* bytes per group   */
+  const uint32_t C = p.geo.channels;
+  const uint32_t spb = p.geo.samples_per_block;
+  const uint32_t bs = p.geo.block_size;
+
+  const uint64_t units_per_stream = (uint64_t)(p.block_end - p.block_begin) * C;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stream = t / units_per_stream;
+  if (stream >= p.num_streams) return;
+  const uint32_t r = (uint32_t)(t % units_per_stream);
+  const uint32_t b = p.block_begin + r / C;
+  const uint32_t ch = r % C;
+
+  const uint8_t *slot = p.aad + stream * p.aad_stride;
+  const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
+  uint32_t ns = p.uniform_samples;
+  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  if ((uint64_t)b * spb >= ns) return;
+  const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+  /* a block whose channel headers are not all present is not decoded (src/aad_decoder.c:347) */
+  if (blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C > size) return;
+  const uint32_t avail = (uint32_t)min((uint64_t)bs, (uint64_t)size - blk_off);
+  const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+  const uint32_t want = min(spb, buf - b * spb);
+
+  const uint8_t *blk = slot + blk_off;
+  auto rd = [&](uint32_t pos) -> uint32_t { return pos < avail ? (uint32_t)blk[pos] : 0u; };
+
+  Chain c;
+  {
+    const uint32_t hp = ch * AADF_CHANNEL_HEADER_BYTES;
+    const uint32_t head = (rd(hp) << 8) | rd(hp + 1);
+    c.idx = (int32_t)(int16_t)(head >> 4);
+    const uint32_t shift = head & 0xFu;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t w = (rd(hp + 2 + 4 * k) << 8) | rd(hp + 3 + 4 * k);
+      const uint32_t s = (rd(hp + 4 + 4 * k) << 8) | rd(hp + 5 + 4 * k);
+      c.w[k] = (int32_t)((uint32_t)(int32_t)(int16_t)w << shift);
+      c.h[k] = (int32_t)(int16_t)s;
+    }
+  }
+
+  const uint64_t out_base = stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+  int16_t *out16 = (int16_t *)p.pcm + out_base;
+  int32_t *out32 = (int32_t *)p.pcm + out_base;
+  auto put = [&](uint32_t i, int32_t v) {
+    if (i < want) {
+      if (p.out32) out32[i] = v; else out16[i] = (int16_t)v;
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < 4; i++) put(i, c.h[3 - i]);
+
+  const uint32_t data0 = C * AADF_CHANNEL_HEADER_BYTES;
+  uint32_t g = 0;
+  for (uint32_t i = AADF_TAPS; i < want; i += GS, g++) {
+    const uint32_t pos = data0 + (g * C + ch) * GB;
+    uint32_t packed = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < GB; k++) packed = (packed << 8) | rd(pos + k);
+#pragma unroll
+    for (uint32_t j = 0; j < GS; j++) {
+      const uint32_t code = (packed >> (BITS * (GS - 1 - j))) & ((1u << BITS) - 1u);
+      put(i + j, chain_decode<BITS>(c, code, tab));
+    }
+  }
+}
+
+/* mid/side -> left/right over decoded output (src/aad_decoder.c:458-470), generic path only */
+__global__ void aad_ms_to_lr(const aadk_decode_params p)
+{
+  const uint32_t spb = p.geo.samples_per_block;
+  const uint64_t per_stream = (uint64_t)(p.block_end - p.block_begin) * spb;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stream = t / per_stream;
+  if (stream >= p.num_streams) return;
+  const uint64_t s = (uint64_t)p.block_begin * spb + t % per_stream;
+  const uint32_t b = (uint32_t)(s / spb);
+  const uint32_t C = p.geo.channels;
+  const uint8_t *slot = p.aad + stream * p.aad_stride;
+  const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
+  uint32_t ns = p.uniform_samples;
+  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  if ((uint64_t)b * spb >= ns) return;
+  const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * p.geo.block_size;
+  if (blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C > size) return;
+  const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+  if (s >= buf) return;
+  const uint64_t i0 = stream * p.pcm_clip_stride + s;
+  const uint64_t i1 = i0 + p.pcm_ch_stride;
+  if (p.out32) {
+    int32_t *o = (int32_t *)p.pcm;
+    const int32_t m = o[i0], d = o[i1];
+    o[i0] = clamp16(m + d);
+    o[i1] = clamp16(m - d);
+  } else {
+    int16_t *o = (int16_t *)p.pcm;
+    const int32_t m = o[i0], d = o[i1];
+    o[i0] = (int16_t)clamp16(m + d);
+    o[i1] = (int16_t)clamp16(m - d);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * encode, generic path.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Sample source for one (stream, channel): int16 or int32 planar PCM, optional LR->MS on the
+ * fly (src/aad_encoder.c:413-428), zero beyond `limit` (src/aad_encoder.c:592-593). */
+struct SampleSource {
+  const int16_t *a16, *b16;
+  const int32_t *a32, *b32;
+  int mode; /* 0 plain, 1 mid, 2 side */
+
+  __device__ __forceinline__ int32_t raw(const int16_t *p16, const int32_t *p32, uint32_t i) const
+  {
+    return p32 ? (int32_t)(int16_t)p32[i] : (int32_t)p16[i];
+  }
+  __device__ __forceinline__ int32_t at(uint32_t i, uint32_t limit) const
+  {
+    if (i >= limit) return 0;
+    const int32_t x = raw(a16, a32, i);
+    if (mode == 0) return x;
+    const int32_t y = raw(b16, b32, i);
+    return clamp16(mode == 1 ? (x + y) >> 1 : (x - y) >> 1);
+  }
+};
+
+/* src/aad_encoder.c:431-467: dry run over samples [first, first+n) starting from c. */
+template <int BITS>
+__device__ __forceinline__ double trial_rmse(Chain &c, const SampleSource &src, uint32_t first, uint32_t n,
+                                             const SharedTables &tab)
+{
+  if (n < AADF_TAPS) return 0.0;
+  const uint32_t limit = first + n;
+#pragma unroll
+  for (int k = 0; k < 4; k++) c.h[3 - k] = src.at(first + k, limit);
+  long long sum = 0;   /* exact: |term| < 2^31, n < 2^16 */
+  for (uint32_t i = first + AADF_TAPS; i < limit; i++) {
+    int32_t q;
+    chain_encode<BITS>(c, src.at(i, limit), tab, q);
+    sum += (long long)wmul(q, q);   /* 32-bit wrapping product, as compiled in the reference */
+  }
+  return sqrt((double)sum / (double)n);
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_params p)
+{
+  __shared__ SharedTables tab;
+  load_tables<BITS>(tab);
+
+  constexpr uint32_t GS = (BITS == 4) ? 2 : (BITS == 3 ? 8 : 4);
+  constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
+  const uint32_t C = p.geo.channels;
+  const uint32_t spb = p.geo.samples_per_block;
+  const uint32_t bs = p.geo.block_size;
+
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stream = t / C;
+  if (stream >= p.num_streams) return;
+  const uint32_t ch = (uint32_t)(t % C);
+  const uint32_t ns = p.num_samples ? p.num_samples[stream] : p.uniform_samples;
+
+  uint8_t *out = p.aad + stream * p.aad_stride;
+  if (ch == 0 && p.block_begin == 0) {
+    if (ns > 0) aadf_write_file_header(out, C, ns, p.sampling_rate, BITS, bs, spb, p.geo.ms);
+    if (p.out_sizes) p.out_sizes[stream] = ns ? (uint32_t)aadf_stream_bytes(ns, C, BITS, bs, spb) : 0u;
+  }
+
+  SampleSource src;
+  {
+    const uint64_t base = stream * p.pcm_clip_stride;
+    const bool ms = p.geo.ms && C >= 2 && ch < 2;
+    const uint64_t off_a = base + (uint64_t)(ms ? 0 : ch) * p.pcm_ch_stride;
+    const uint64_t off_b = base + p.pcm_ch_stride;
+    src.a16 = p.in32 ? nullptr : (const int16_t *)p.pcm + off_a;
+    src.b16 = p.in32 ? nullptr : (const int16_t *)p.pcm + off_b;
+    src.a32 = p.in32 ? (const int32_t *)p.pcm + off_a : nullptr;
+    src.b32 = p.in32 ? (const int32_t *)p.pcm + off_b : nullptr;
+    src.mode = ms ? (ch == 0 ? 1 : 2) : 0;
+  }
+
+  Chain c;
+  const uint64_t st = (stream * C + ch) * AADK_STATE_WORDS;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    c.h[k] = 0;
+    c.w[k] = p.state_in ? p.state_in[st + k] : 0;
+  }
+  c.idx = p.state_in ? p.state_in[st + 4] : 0;
+
+  const uint32_t nblk = min(aadf_num_blocks(ns, spb), p.block_end);
+  for (uint32_t b = p.block_begin; b < nblk; b++) {
+    const uint32_t first = b * spb;
+    const uint32_t n = min(spb, ns - first);
+    const uint32_t limit = first + n;
+
+    if (p.trials > 0) {   /* src/aad_encoder.c:470-562 */
+      Chain probe = c, best = c, run = c;
+      double best_rmse = trial_rmse<BITS>(probe, src, first, n, tab);
+      for (uint32_t tr = 0; tr < p.trials; tr++) {
+        if (b > 0) (void)trial_rmse<BITS>(run, src, first - spb, spb, tab);
+        const Chain cand = run;
+        const double rmse = trial_rmse<BITS>(run, src, first, n, tab);
+        if (best_rmse > rmse) { best_rmse = rmse; best = cand; }
+      }
+      c = best;
+    }
+
+    /* block header, src/aad_encoder.c:606-655 */
+#pragma unroll
+    for (int k = 0; k < 4; k++) c.h[3 - k] = src.at(first + k, limit);
+    int32_t maxabs = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) maxabs = max(maxabs, c.w[k] >= 0 ? c.w[k] : wsub(0, c.w[k]));
+    uint32_t shift = 0;
+    while (maxabs > 32767) { maxabs >>= 1; shift++; }
+    const int32_t keep = (int32_t)~((1u << shift) - 1u);
+#pragma unroll
+    for (int k = 0; k < 4; k++) c.w[k] &= keep;
+    uint8_t *blk = out + AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+    uint8_t *hp = blk + ch * AADF_CHANNEL_HEADER_BYTES;
+    aadf_put_be16(hp, (((uint32_t)c.idx << 4) | (shift & 0xFu)) & 0xFFFFu);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      aadf_put_be16(hp + 2 + 4 * k, (uint32_t)(c.w[k] >> shift) & 0xFFFFu);
+      aadf_put_be16(hp + 4 + 4 * k, (uint32_t)c.h[k] & 0xFFFFu);
+    }
+
+    /* code groups, src/aad_encoder.c:661-722 */
+    uint8_t *dp = blk + C * AADF_CHANNEL_HEADER_BYTES + ch * GB;
+    for (uint32_t i = first + AADF_TAPS; i < limit; i += GS, dp += C * GB) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < GS; j++) {
+        int32_t q;
+        packed = (packed << BITS) | chain_encode<BITS>(c, src.at(i + j, limit), tab, q);
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < GB; k++) dp[k] = (uint8_t)(packed >> (8 * (GB - 1 - k)));
+    }
+  }
+
+  if (p.state_out) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) p.state_out[st + k] = c.w[k];
+    p.state_out[st + 4] = c.idx;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * utilities
+ * ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+
+/* x[n] = 0.4*sin(f1) + 0.2*sin(3001 Hz) + uniform noise in [-1000, 1000], integer only.
+ * Mirrored bit-for-bit by aad_b200.synth.synth_pcm16 (numpy). */
+__global__ void aad_synth(const aadk_synth_params p)
+{
+  const uint64_t per_stream = (uint64_t)p.channels * p.num_samples;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stream = t / per_stream;
+  if (stream >= p.num_streams) return;
+  const uint32_t r = (uint32_t)(t % per_stream);
+  const uint32_t ch = r / p.num_samples;
+  const uint32_t n = r % p.num_samples;
+  const uint32_t gi = p.first_stream + (uint32_t)stream;
+  const uint32_t f1 = 440u * (1u + ch) + 7u * (gi % 97u);
+  const uint32_t p1 = (uint32_t)(((uint64_t)f1 << 32) / p.sampling_rate);
+  const uint32_t p2 = (uint32_t)((3001ull << 32) / p.sampling_rate);
+  const uint32_t seed = 0x9E3779B9u ^ (gi * 2654435761u + ch * 40503u + 1u);
+  const int32_t s1 = p.lut[(n * p1) >> 22];
+  const int32_t s2 = p.lut[(n * p2) >> 22];
+  const int32_t noise = (int32_t)(mix32(seed ^ (n * 0x9E3779B1u)) % 2001u) - 1000;
+  const int32_t x = ((s1 * 13107) >> 15) + ((s2 * 6553) >> 15) + noise;
+  p.pcm[stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + n] = (int16_t)clamp16(x);
+}
+
+__global__ void aad_deinterleave16(const int16_t *__restrict__ in, int16_t *__restrict__ out, uint64_t ch_stride,
+                                   uint32_t channels, uint32_t num_samples)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)channels * num_samples) return;
+  const uint32_t s = (uint32_t)(t / channels), c = (uint32_t)(t % channels);
+  out[(uint64_t)c * ch_stride + s] = in[t];
+}
+
+__global__ void aad_interleave16(const int16_t *__restrict__ in, uint64_t ch_stride, int16_t *__restrict__ out,
+                                 uint32_t channels, uint32_t num_samples)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)channels * num_samples) return;
+  const uint32_t s = (uint32_t)(t / channels), c = (uint32_t)(t % channels);
+  out[t] = in[(uint64_t)c * ch_stride + s];
+}
+
+inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
+
+}  // namespace
+
+extern "C" {
+
+uint64_t aadk_launch_count(void) { return g_launches; }
+
+int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->block_end <= p->block_begin) return 0;
+  const uint64_t threads = (uint64_t)p->num_streams * (p->block_end - p->block_begin) * p->geo.channels;
+  if (threads == 0) return 0;
+  const unsigned block = 128, grid = grid_for(threads, block);
+  switch (p->geo.bits) {
+    case 4: aad_decode_generic<4><<<grid, block, 0, s>>>(*p); break;
+    case 3: aad_decode_generic<3><<<grid, block, 0, s>>>(*p); break;
+    case 2: aad_decode_generic<2><<<grid, block, 0, s>>>(*p); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  g_launches++;
+  if (p->geo.ms && p->geo.channels >= 2) {
+    const uint64_t n = (uint64_t)p->num_streams * (p->block_end - p->block_begin) * p->geo.samples_per_block;
+    aad_ms_to_lr<<<grid_for(n, 256), 256, 0, s>>>(*p);
+    g_launches++;
+  }
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_encode(const struct aadk_encode_params *p, void *stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t threads = (uint64_t)p->num_streams * p->geo.channels;
+  if (threads == 0 || p->block_end <= p->block_begin) return 0;
+  const unsigned block = 128, grid = grid_for(threads, block);
+  switch (p->geo.bits) {
+    case 4: aad_encode_generic<4><<<grid, block, 0, s>>>(*p); break;
+    case 3: aad_encode_generic<3><<<grid, block, 0, s>>>(*p); break;
+    case 2: aad_encode_generic<2><<<grid, block, 0, s>>>(*p); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_synth(const struct aadk_synth_params *p, void *stream)
+{
+  const uint64_t n = (uint64_t)p->num_streams * p->channels * p->num_samples;
+  if (n == 0) return 0;
+  aad_synth<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_deinterleave16(const int16_t *interleaved, int16_t *planar, uint64_t ch_stride, uint32_t channels,
+                               uint32_t num_samples, void *stream)
+{
+  const uint64_t n = (uint64_t)channels * num_samples;
+  if (n == 0) return 0;
+  aad_deinterleave16<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(interleaved, planar, ch_stride, channels,
+                                                                         num_samples);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_interleave16(const int16_t *planar, uint64_t ch_stride, int16_t *interleaved, uint32_t channels,
+                             uint32_t num_samples, void *stream)
+{
+  const uint64_t n = (uint64_t)channels * num_samples;
+  if (n == 0) return 0;
+  aad_interleave16<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(planar, ch_stride, interleaved, channels,
+                                                                       num_samples);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

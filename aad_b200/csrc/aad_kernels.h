@@ -1,0 +1,89 @@
+/*
+ * aad_kernels.h -- the thin C ABI between the C host code and the sm_100a kernels.
+ * Plain pointers and sizes only; every pointer in the *_params structs is a DEVICE
+ * pointer, `stream` is a cudaStream_t passed as void*.  Launchers return a cudaError_t
+ * value as int (0 = success) and never synchronise.
+ */
+#ifndef AAD_KERNELS_H
+#define AAD_KERNELS_H
+
+#include <stdint.h>
+#include "aad_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One chain = one (stream, channel).  Encoder state carried between blocks / calls:
+ * weight[4] then stepsize_index (src/aad_encoder.c:10-15). */
+#define AADK_STATE_WORDS 5
+
+struct aadk_decode_params {
+  const uint8_t *aad;          /* stream i starts (file header included) at aad + i*aad_stride */
+  uint64_t aad_stride;
+  const uint32_t *sizes;       /* valid bytes per stream, or NULL -> uniform_size */
+  uint32_t uniform_size;
+  uint32_t num_streams;
+  struct aadf_geometry geo;
+  uint32_t block_begin;        /* blocks [block_begin, block_end) of every stream are decoded */
+  uint32_t block_end;
+  uint32_t uniform_samples;    /* samples per channel when read_headers == 0 */
+  uint32_t read_headers;       /* 1: take num_samples from each stream's own 31-byte header */
+  uint32_t buf_samples;        /* output capacity per channel (reference DecodeWhole semantics); 0 = num_samples */
+  void *pcm;                   /* planar: sample s of channel c of stream i at i*clip_stride + c*ch_stride + s */
+  uint64_t pcm_clip_stride;    /* in samples */
+  uint64_t pcm_ch_stride;      /* in samples */
+  uint32_t out32;              /* 0: int16 samples, 1: int32 samples (the reference API type) */
+};
+
+struct aadk_encode_params {
+  const void *pcm;             /* planar, same addressing as the decoder's output */
+  uint64_t pcm_clip_stride;
+  uint64_t pcm_ch_stride;
+  uint32_t in32;               /* 0: int16 samples, 1: int32 samples holding int16-range values */
+  const uint32_t *num_samples; /* per stream, or NULL -> uniform_samples */
+  uint32_t uniform_samples;
+  uint32_t num_streams;
+  struct aadf_geometry geo;
+  uint32_t sampling_rate;
+  uint32_t trials;             /* num_encode_trials, src/aad_encoder.h:14 */
+  uint8_t *aad;                /* stream i written (file header included) at aad + i*aad_stride */
+  uint64_t aad_stride;         /* >= aadf_stream_bytes_bound() */
+  uint32_t *out_sizes;         /* bytes written per stream, nullable */
+  const int32_t *state_in;     /* [stream][channel][AADK_STATE_WORDS], NULL = all zero */
+  int32_t *state_out;          /* same shape, nullable */
+  uint32_t block_begin;        /* blocks [block_begin, block_end) of every stream are encoded; the */
+  uint32_t block_end;          /* chain state enters through state_in and leaves through state_out */
+};
+
+int aadk_launch_decode(const struct aadk_decode_params *p, void *stream);
+int aadk_launch_encode(const struct aadk_encode_params *p, void *stream);
+
+/* Deterministic integer-only synthetic PCM (bench / tests): SURVEY.md 8(d).
+ * lut = 1024-entry int16 sine table (device). */
+struct aadk_synth_params {
+  int16_t *pcm;
+  uint64_t pcm_clip_stride;
+  uint64_t pcm_ch_stride;
+  uint32_t num_streams;
+  uint32_t channels;
+  uint32_t num_samples;
+  uint32_t sampling_rate;
+  uint32_t first_stream;       /* global index of stream 0 (so shards generate their own slice) */
+  const int16_t *lut;
+};
+int aadk_launch_synth(const struct aadk_synth_params *p, void *stream);
+
+/* PCM16 interleaved (WAV order) <-> planar, src/main.c:122-126,175-179 done on the device */
+int aadk_launch_deinterleave16(const int16_t *interleaved, int16_t *planar, uint64_t ch_stride, uint32_t channels,
+                               uint32_t num_samples, void *stream);
+int aadk_launch_interleave16(const int16_t *planar, uint64_t ch_stride, int16_t *interleaved, uint32_t channels,
+                             uint32_t num_samples, void *stream);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t aadk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

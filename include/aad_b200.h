@@ -1,0 +1,99 @@
+/*
+ * aad_b200.h -- extended C ABI of libaad_b200.so: the same ADPCM hot path as the drop-in
+ * API (aad_encoder.h / aad_decoder.h), exposed in the shapes a GPU wants:
+ *
+ *   - batches of independent streams ("clips") in one call   (BASELINE config 5)
+ *   - int16 PCM at the boundary (what a 16-bit WAV holds) instead of int32
+ *   - device-resident entry points (no host copies) for callers that already live on the GPU
+ *   - host entry points that pipeline H2D / kernels / D2H in chunks over pinned staging
+ *
+ * There is no CPU fallback: every entry point returns AAD_APIRESULT_NG (and
+ * AADGpu_LastError() says why) when no CUDA device is usable.
+ *
+ * Reference interfaces this extends: AADEncoder_EncodeWhole (src/aad_encoder.h:47-50),
+ * AADDecoder_DecodeWhole (src/aad_decoder.h:39-42); parameter meaning follows
+ * struct AADEncodeParameter (src/aad_encoder.h:8-15) and struct AADHeaderInfo
+ * (src/aad.h:43-53).
+ */
+#ifndef AAD_B200_H
+#define AAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "aad.h"
+#include "aad_encoder.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct AADGpu;   /* one CUDA device: streams, staging buffers, scratch */
+
+/* Shape of a batch of streams.  Stream i's planar int16 PCM starts at
+ * pcm + i*pcm_stream_stride; its channel c at + c*pcm_channel_stride (both in samples).
+ * Stream i's encoded bytes (31-byte file header included) start at aad + i*aad_stream_stride. */
+struct AADGpuBatch {
+  uint32_t num_streams;
+  uint32_t num_samples;                       /* per channel; the maximum when lengths are ragged */
+  struct AADEncodeParameter param;            /* channels, rate, bits, max block size, MS, trials */
+  uint64_t pcm_stream_stride;                 /* samples */
+  uint64_t pcm_channel_stride;                /* samples */
+  uint64_t aad_stream_stride;                 /* bytes, >= AADGpu_StreamBytesBound() */
+};
+
+/* ---- device / context ------------------------------------------------------------------ */
+int  AADGpu_DeviceCount(void);                           /* 0 when CUDA is unusable */
+struct AADGpu *AADGpu_Create(int device);                /* NULL on failure */
+void AADGpu_Destroy(struct AADGpu *gpu);
+const char *AADGpu_LastError(void);                      /* thread-local, never NULL */
+uint64_t AADGpu_KernelLaunchCount(void);                 /* kernels launched by this library so far */
+void AADGpu_SetMaxChannels(uint32_t max_channels);       /* 2 = stock reference limit, 8 = default */
+uint32_t AADGpu_GetMaxChannels(void);
+
+/* pinned host memory for the host entry points (plain malloc'd memory works too, slower) */
+void *AADGpu_HostAlloc(size_t bytes);
+void  AADGpu_HostFree(void *p);
+
+/* ---- sizing helpers (pure arithmetic) -------------------------------------------------- */
+/* worst-case encoded bytes of one stream (file header + every block full) */
+uint64_t AADGpu_StreamBytesBound(const struct AADEncodeParameter *param, uint32_t num_samples);
+/* exact encoded bytes of one stream */
+uint64_t AADGpu_StreamBytes(const struct AADEncodeParameter *param, uint32_t num_samples);
+
+/* ---- device-resident hot path (all pointers are device pointers on gpu's device) -------- */
+/* num_samples_dev / sizes_dev: per-stream lengths, NULL = uniform (batch->num_samples / full
+ * streams).  out_sizes_dev nullable.  `stream` is a cudaStream_t (NULL = default stream); the
+ * calls only enqueue work. */
+AADApiResult AADGpu_EncodeBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
+                                      const int16_t *pcm_dev, const uint32_t *num_samples_dev,
+                                      uint8_t *aad_dev, uint32_t *out_sizes_dev, void *stream);
+/* Each stream's length is taken from its own file header; sizes_dev (nullable) bounds the
+ * valid bytes per stream.  param.num_encode_trials is ignored. */
+AADApiResult AADGpu_DecodeBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
+                                      const uint8_t *aad_dev, const uint32_t *sizes_dev,
+                                      int16_t *pcm_dev, void *stream);
+
+/* ---- host entry points: H2D -> kernels -> D2H, chunked and overlapped ------------------- */
+/* num_samples / sizes: host arrays or NULL (uniform).  out_sizes: host array or NULL. */
+AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch,
+                                const int16_t *pcm, const uint32_t *num_samples,
+                                uint8_t *aad, uint32_t *out_sizes);
+AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch,
+                                const uint8_t *aad, const uint32_t *sizes, int16_t *pcm);
+
+/* ---- deterministic synthetic PCM (bench / tests), SURVEY.md 8(d) ------------------------ */
+AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
+                                     uint32_t first_stream, int16_t *pcm_dev, void *stream);
+
+/* ---- WAV-order helpers on the device (src/main.c:122-126,175-179) ----------------------- */
+AADApiResult AADGpu_Deinterleave16Device(struct AADGpu *gpu, const int16_t *interleaved_dev, int16_t *planar_dev,
+                                         uint64_t channel_stride, uint32_t channels, uint32_t num_samples,
+                                         void *stream);
+AADApiResult AADGpu_Interleave16Device(struct AADGpu *gpu, const int16_t *planar_dev, uint64_t channel_stride,
+                                       int16_t *interleaved_dev, uint32_t channels, uint32_t num_samples,
+                                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAD_B200_H */
