@@ -1,0 +1,252 @@
+"""Parity of the CUDA path (through the C ABI of libaad_b200.so) with the reference -- GPU only.
+
+Bar: bit-exact.  Identical .aad bytes on encode, identical PCM on decode, for every bit depth,
+channel count, block size, MS setting and trial count the reference supports, on the reference's
+own fixtures, on the golden table generated from the compiled reference, and differentially
+against the oracle (and the compiled reference, when oracle/_ref travelled) on seeded inputs
+including the pathological signals that wrap int32 (test/test_aad_encode_decode.c:447-470).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import aadtest
+from aad_b200 import capi
+from aad_b200.capi import OK, make_param
+
+pytestmark = pytest.mark.gpu
+
+
+def _case_pcm(case):
+    kind, name = case["source"].split(":")
+    if kind == "wav":
+        return aadtest.read_wav16(aadtest.GOLDEN / f"{name}.wav")
+    return aadtest.signal(name, case["channels"], case["n"], case["seed"]), case["rate"]
+
+
+# ---- the reference's own fixtures through the drop-in API ---------------------------------------
+
+@pytest.mark.parametrize("stem", ["sin300Hz", "sin300Hz_mono"])
+def test_shipped_fixtures_bit_exact(product, gpu_ctx, stem):
+    api, _ = product
+    pcm, rate = aadtest.read_wav16(aadtest.GOLDEN / f"{stem}.wav")
+    golden_aad = (aadtest.GOLDEN / f"{stem}.aad").read_bytes()
+    golden_dec, _ = aadtest.read_wav16(aadtest.GOLDEN / f"{stem}_decoded.wav")
+    rc, data = api.encode_whole(pcm, rate, 4, 1024, False, 2)       # CLI defaults, test/make_test_data.sh:4-5
+    assert rc == OK and data == golden_aad
+    rc, dec, h = api.decode_whole(golden_aad)                        # test/test_aad_decoder.c:256-328
+    assert rc == OK and h.num_channels == pcm.shape[0]
+    assert np.array_equal(dec, golden_dec.astype(np.int32))
+
+
+def test_golden_table_through_dropin_api(product, gpu_ctx):
+    api, _ = product
+    for case in aadtest.golden_table():
+        pcm, rate = _case_pcm(case)
+        rc, data = api.encode_whole(pcm, rate, case["bits"], case["max_block"], case["ms"], case["trials"])
+        assert rc == OK, case
+        assert len(data) == case["aad_size"] and aadtest.sha(data) == case["aad_sha"], case
+        rc, dec, _ = api.decode_whole(data)
+        assert rc == OK and aadtest.pcm_sha(dec.astype(np.int16)) == case["pcm_sha"], case
+
+
+def test_five_bits_is_rejected_like_the_reference(product, gpu_ctx):
+    api, gpu = product
+    pcm = aadtest.signal("sine", 1, 500)
+    assert api.encode_whole(pcm, 8000, 5)[0] == capi.INVALID_FORMAT          # src/aad_encoder.c:743-746
+    assert api.encode_whole(pcm, 8000, 1)[0] == capi.INVALID_FORMAT          # src/aad_encoder.c:165-168
+    with pytest.raises(Exception):
+        gpu.encode_batch(gpu_ctx, pcm[None], 8000, 5)
+
+
+# ---- differential against the oracle ------------------------------------------------------------
+
+def _random_cases(n_cases, seed, max_channels=8):
+    rng = np.random.default_rng(seed)
+    for i in range(n_cases):
+        ch = int(rng.choice([1, 1, 2, 2, 2, 3, 4, 8])) if max_channels > 2 else int(rng.integers(1, 3))
+        yield dict(kind=aadtest.SIGNALS[int(rng.integers(len(aadtest.SIGNALS)))], ch=ch,
+                   n=int(rng.choice([1, 3, 4, 5, 9, 100, 2016, 2017, 4100, 9001])) if i % 3 else int(rng.integers(1, 12000)),
+                   bits=int(rng.integers(2, 5)), block=int(rng.choice([18 * ch + 8, 128, 256, 1024, 4096])) if ch <= 2 else 1024,
+                   ms=bool(rng.integers(2)) and ch >= 2, trials=int(rng.integers(0, 4)), seed=1000 + i)
+
+
+def test_dropin_api_matches_oracle_on_random_cases(product, gpu_ctx, oracle):
+    api, _ = product
+    for c in _random_cases(150, seed=21):
+        pcm = aadtest.signal(c["kind"], c["ch"], c["n"], c["seed"])
+        rc_o, want = oracle.encode(pcm, 44100, c["bits"], c["block"], c["ms"], c["trials"])
+        rc_g, got = api.encode_whole(pcm, 44100, c["bits"], c["block"], c["ms"], c["trials"])
+        assert rc_g == rc_o, c
+        if rc_o != 0:
+            continue
+        assert got == want, c
+        rc_o, dec_o, _ = oracle.decode(want)
+        rc_g, dec_g, _ = api.decode_whole(want)
+        assert rc_g == rc_o == 0 and np.array_equal(dec_g, dec_o.astype(np.int32)), c
+
+
+def test_dropin_api_matches_compiled_reference(product, gpu_ctx, ref):
+    api, _ = product
+    for c in _random_cases(60, seed=22, max_channels=2):
+        pcm = aadtest.signal(c["kind"], c["ch"], c["n"], c["seed"])
+        rc_r, want = ref.encode_whole(pcm, 48000, c["bits"], c["block"], c["ms"], c["trials"])
+        rc_g, got = api.encode_whole(pcm, 48000, c["bits"], c["block"], c["ms"], c["trials"])
+        assert rc_g == rc_r and got == want, c
+        if rc_r == OK:
+            _, dec_r, _ = ref.decode_whole(want)
+            _, dec_g, _ = api.decode_whole(want)
+            assert np.array_equal(dec_g, dec_r), c
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("channels,ms", [(1, False), (2, False), (2, True), (8, False)])
+def test_batch_api_matches_oracle(product, gpu_ctx, oracle, bits, channels, ms):
+    """Many streams per call, ragged lengths, trials 2 (the CLI default)."""
+    _, gpu = product
+    n_streams, n_max = 37, 5200
+    rng = np.random.default_rng(bits * 10 + channels)
+    lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+    lens[0], lens[1], lens[2] = n_max, 3, 4
+    pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+    for i in range(n_streams):
+        pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], channels, int(lens[i]), i)
+    aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, 1024, ms, 2, num_samples=lens)
+    for i in range(n_streams):
+        rc, want = oracle.encode(pcm[i, :, :lens[i]], 44100, bits, 1024, ms, 2)
+        assert rc == 0 and sizes[i] == len(want), (i, lens[i])
+        assert aad[i, :sizes[i]].tobytes() == want, (i, lens[i])
+    dec = gpu.decode_batch(gpu_ctx, aad, n_max, 44100, channels, bits, 1024, ms, sizes=sizes)
+    for i in range(n_streams):
+        _, want, _ = oracle.decode(aad[i, :sizes[i]].tobytes())
+        assert np.array_equal(dec[i, :, :lens[i]], want), (i, lens[i])
+
+
+def test_trials_zero_and_many(product, gpu_ctx, oracle):
+    _, gpu = product
+    pcm = np.stack([aadtest.signal(k, 2, 7000, 5) for k in aadtest.SIGNALS])
+    for trials in (0, 1, 5):
+        aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 48000, 4, 1024, False, trials)
+        for i in range(len(pcm)):
+            _, want = oracle.encode(pcm[i], 48000, 4, 1024, False, trials)
+            assert aad[i, :sizes[i]].tobytes() == want, (trials, i)
+
+
+# ---- API semantics that need the device -----------------------------------------------------------
+
+def test_handle_reuse_carries_state(product, gpu_ctx, oracle):
+    """src/aad_encoder.c:299-301,797-799: weights survive between EncodeWhole calls on one handle."""
+    api, _ = product
+    a, b = aadtest.signal("music", 2, 3000, 1), aadtest.signal("sine", 2, 2500, 2)
+    h = api.lib.AADEncoder_Create(1024, None, 0)
+    assert api.lib.AADEncoder_SetEncodeParameter(h, C.byref(make_param(2, 44100, 4, 1024, False, 1))) == OK
+    _, ga = api.encode_whole(a, 44100, 4, handle=h)
+    _, gb = api.encode_whole(b, 44100, 4, handle=h)
+    # SetEncodeParameter resets the step index but not the weights
+    assert api.lib.AADEncoder_SetEncodeParameter(h, C.byref(make_param(2, 44100, 4, 1024, False, 1))) == OK
+    _, gc = api.encode_whole(a, 44100, 4, handle=h)
+    api.lib.AADEncoder_Destroy(h)
+    state = [[0] * 5, [0] * 5]
+    _, oa = oracle.encode(a, 44100, 4, 1024, False, 1, state=state)
+    _, ob = oracle.encode(b, 44100, 4, 1024, False, 1, state=state)
+    for s in state:
+        s[4] = 0
+    _, oc = oracle.encode(a, 44100, 4, 1024, False, 1, state=state)
+    assert ga == oa and gb == ob and gc == oc
+
+
+def test_decode_block_and_oversized_buffer(product, gpu_ctx, oracle):
+    api, _ = product
+    pcm = aadtest.signal("music", 2, 3000, 7)
+    _, data = oracle.encode(pcm, 44100, 3, 1024, True, 1)
+    rc, h = api.decode_header(data)
+    dec = api.lib.AADDecoder_Create(None, 0)
+    assert api.lib.AADDecoder_SetHeader(dec, C.byref(h)) == OK
+    _, want, _ = oracle.decode(data)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    spb, bs = h.num_samples_per_block, h.block_size
+    for b, room in [(0, spb), (1, spb), (1, 100), (2, 3000 - 2 * spb), (0, 3)]:
+        out = np.full((2, spb), -7, dtype=np.int32)
+        n = C.c_uint32()
+        blk = buf[31 + b * bs:31 + (b + 1) * bs]
+        rc = api.lib.AADDecoder_DecodeBlock(dec, blk.ctypes.data_as(C.POINTER(C.c_uint8)), len(blk),
+                                            capi._planar_pointers([out[0], out[1]]), 2, room, C.byref(n))
+        assert rc == OK and n.value == min(spb, room)
+        assert np.array_equal(out[:, :n.value], want[:, b * spb:b * spb + n.value].astype(np.int32))
+        assert (out[:, n.value:] == -7).all()
+    short = buf[31:31 + 20]
+    n = C.c_uint32()
+    out = np.zeros((2, spb), dtype=np.int32)
+    assert api.lib.AADDecoder_DecodeBlock(dec, short.ctypes.data_as(C.POINTER(C.c_uint8)), 20,
+                                          capi._planar_pointers([out[0], out[1]]), 2, spb, C.byref(n)) == capi.INSUFFICIENT_DATA
+    api.lib.AADDecoder_Destroy(dec)
+    # DecodeWhole with a buffer larger than the stream: only num_samples are defined by the format;
+    # the oracle and the product agree on the whole buffer when the tail reads as zero bytes
+    rc_g, big_g, _ = api.decode_whole(data, buf_samples=3000 + 50, fill=-9)
+    rc_o, big_o, _ = oracle.decode(data, buf_samples=3000 + 50, fill=-9)
+    assert rc_g == rc_o == 0 and np.array_equal(big_g, big_o.astype(np.int32))
+
+
+def test_truncated_stream(product, gpu_ctx, oracle):
+    api, _ = product
+    pcm = aadtest.signal("music", 1, 9000, 3)
+    _, data = oracle.encode(pcm, 44100, 4, 1024, False, 0)
+    _, full, _ = oracle.decode(data)
+    # cut inside block 2's header: blocks 0,1 decode, then INSUFFICIENT_DATA (src/aad_decoder.c:347,522-527)
+    cut = data[:31 + 2 * 1024 + 10]
+    rc_g, dec_g, _ = api.decode_whole(cut, fill=-5)
+    rc_o, dec_o, _ = oracle.decode(cut, fill=-5)
+    assert rc_g == rc_o == capi.INSUFFICIENT_DATA
+    assert np.array_equal(dec_g, dec_o.astype(np.int32))
+    assert np.array_equal(dec_g[:, :2 * 2016], full[:, :2 * 2016].astype(np.int32))
+    # cut at a block boundary: a clean shorter decode
+    cut = data[:31 + 3 * 1024]
+    rc_g, dec_g, _ = api.decode_whole(cut, fill=-5)
+    rc_o, dec_o, _ = oracle.decode(cut, fill=-5)
+    assert rc_g == rc_o == 0 and np.array_equal(dec_g, dec_o.astype(np.int32))
+
+
+# ---- device-resident entry points (torch only provides the memory) ---------------------------------
+
+def test_device_resident_roundtrip_and_synth(product, gpu_ctx, oracle):
+    import torch
+    from aad_b200.synth import synth_pcm16
+    _, gpu = product
+    n_streams, ch, n = 64, 2, 30000
+    prm = make_param(ch, 44100, 4, 1024, False, 2)
+    b = gpu.batch(n_streams, n, prm)
+    dev = torch.device("cuda:0")
+    pcm = torch.zeros((n_streams, ch, n), dtype=torch.int16, device=dev)
+    aad = torch.zeros((n_streams, b.aad_stream_stride), dtype=torch.uint8, device=dev)
+    sizes = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    out = torch.zeros_like(pcm)
+    stream = torch.cuda.current_stream().cuda_stream
+    launches = gpu.launch_count()
+    assert gpu.lib.AADGpu_SynthBatchDevice(gpu_ctx, C.byref(b), 100, pcm.data_ptr(), stream) == OK
+    assert gpu.lib.AADGpu_EncodeBatchDevice(gpu_ctx, C.byref(b), pcm.data_ptr(), None, aad.data_ptr(), sizes.data_ptr(),
+                                            stream) == OK
+    assert gpu.lib.AADGpu_DecodeBatchDevice(gpu_ctx, C.byref(b), aad.data_ptr(), None, out.data_ptr(), stream) == OK
+    torch.cuda.synchronize()
+    assert gpu.launch_count() - launches == 3
+    host = pcm.cpu().numpy()
+    assert np.array_equal(host, synth_pcm16(gpu.synth_lut(), 100, n_streams, ch, n, 44100))
+    aad_h, sizes_h, out_h = aad.cpu().numpy(), sizes.cpu().numpy(), out.cpu().numpy()
+    for i in (0, 1, 31, 63):
+        _, want = oracle.encode(host[i], 44100, 4, 1024, False, 2)
+        assert sizes_h[i] == len(want) and aad_h[i, :len(want)].tobytes() == want
+        _, dec, _ = oracle.decode(want)
+        assert np.array_equal(out_h[i], dec)
+
+
+def test_interleave_helpers(product, gpu_ctx):
+    import torch
+    _, gpu = product
+    x = torch.randint(-32768, 32767, (5000, 3), dtype=torch.int16, device="cuda:0")
+    planar = torch.zeros((3, 5000), dtype=torch.int16, device="cuda:0")
+    back = torch.zeros_like(x)
+    s = torch.cuda.current_stream().cuda_stream
+    assert gpu.lib.AADGpu_Deinterleave16Device(gpu_ctx, x.data_ptr(), planar.data_ptr(), 5000, 3, 5000, s) == OK
+    assert gpu.lib.AADGpu_Interleave16Device(gpu_ctx, planar.data_ptr(), 5000, back.data_ptr(), 3, 5000, s) == OK
+    torch.cuda.synchronize()
+    assert torch.equal(planar, x.t().contiguous()) and torch.equal(back, x)

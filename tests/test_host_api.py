@@ -1,0 +1,278 @@
+"""Host-side logic of libaad_b200.so on a machine WITHOUT a GPU: the library loads, exports
+every symbol include/*.h declares, and its O(1) host functions (block geometry, stream header,
+handles, parameter validation) behave exactly like the reference's -- the same assertions as
+test/test_aad_encoder.c:23-333 and test/test_aad_decoder.c:33-253, run side by side against the
+compiled reference when it is available.  No compute entry point is called here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from aad_b200 import capi
+from aad_b200.capi import (INSUFFICIENT_DATA, INVALID_ARGUMENT, INVALID_FORMAT, OK, HeaderInfo, block_header_size,
+                           make_param)
+from test_oracle import BLOCK_SIZE_KAT
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol(product):
+    api, gpu = product
+    declared = set()
+    for header in (ROOT / "include").glob("*.h"):
+        text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+        declared |= set(re.findall(r"\b(AAD(?:Encoder|Decoder|Gpu)_\w+)\s*\(", text))
+    assert len(declared) >= 14 + 15
+    for name in sorted(declared):
+        assert hasattr(api.lib, name), f"{name} declared in include/ but not exported"
+    assert set(api.SYMBOLS) <= declared
+
+
+@pytest.mark.parametrize("max_block,ch,bits,bs,spb", BLOCK_SIZE_KAT)
+def test_calculate_block_size_known_answers(product, max_block, ch, bits, bs, spb):
+    assert product[0].calculate_block_size(max_block, ch, bits) == (OK, bs, spb)
+
+
+def test_calculate_block_size_errors(product):
+    api, gpu = product
+    lib = api.lib
+    bs, spb = C.c_uint16(), C.c_uint32()
+    assert lib.AADEncoder_CalculateBlockSize(32, 1, 4, None, None) == INVALID_ARGUMENT
+    assert lib.AADEncoder_CalculateBlockSize(32, 1, 4, None, C.byref(spb)) == INVALID_ARGUMENT
+    assert lib.AADEncoder_CalculateBlockSize(32, 1, 4, C.byref(bs), None) == OK and bs.value == 32
+    assert api.calculate_block_size(block_header_size(1) - 1, 1, 4)[0] == INVALID_FORMAT
+    assert api.calculate_block_size(32, 0, 4)[0] == INVALID_FORMAT
+    assert api.calculate_block_size(1024, gpu.lib.AADGpu_GetMaxChannels() + 1, 4)[0] == INVALID_FORMAT
+    assert api.calculate_block_size(32, 1, 0)[0] == INVALID_FORMAT
+    assert api.calculate_block_size(32, 1, capi.MAX_BITS + 1)[0] == INVALID_FORMAT     # 5 bits: not a format
+
+
+def test_stock_channel_limit_is_selectable(product):
+    api, gpu = product
+    try:
+        gpu.lib.AADGpu_SetMaxChannels(2)
+        assert api.calculate_block_size(1024, 3, 4)[0] == INVALID_FORMAT     # src/aad.h:13
+        assert api.calculate_block_size(1024, 2, 4)[0] == OK
+    finally:
+        gpu.lib.AADGpu_SetMaxChannels(8)
+    assert api.calculate_block_size(1024, 8, 3) == (OK, 1008, 292)
+
+
+def _valid_header(**kw):
+    h = HeaderInfo(0, 0, 1, 1024, 44100, capi.MAX_BITS, 32, 32, capi.CH_NONE)
+    for k, v in kw.items():
+        setattr(h, k, v)
+    return h
+
+
+def _encode_header(api, h, size=capi.HEADER_SIZE):
+    data = np.zeros(64, dtype=np.uint8)
+    rc = api.lib.AADEncoder_EncodeHeader(C.byref(h), data.ctypes.data_as(C.POINTER(C.c_uint8)), size)
+    return rc, data
+
+
+HEADER_REJECTS = [
+    dict(num_channels=0), dict(num_channels=9), dict(num_samples=0), dict(sampling_rate=0), dict(bits_per_sample=0),
+    dict(bits_per_sample=1), dict(bits_per_sample=5), dict(block_size=0), dict(block_size=17), dict(block_size=18),
+    dict(num_samples_per_block=0), dict(ch_process_method=capi.CH_INVALID),
+    dict(num_channels=1, ch_process_method=capi.CH_MS),
+]
+
+
+def test_encode_header_layout_and_errors(product, request):
+    api, _ = product
+    libs = [api]
+    if (ROOT / "oracle" / "_ref" / "libaad_ref.so").exists():
+        libs.append(request.getfixturevalue("ref"))
+    h = _valid_header(num_channels=2, num_samples=0x01020304, sampling_rate=48000, bits_per_sample=3, block_size=1020,
+                      num_samples_per_block=1316, ch_process_method=capi.CH_MS, format_version=99, codec_version=77)
+    images = []
+    for lib in libs:
+        rc, data = _encode_header(lib, h)
+        assert rc == OK
+        images.append(bytes(data[:31]))
+    d = images[0]
+    assert all(img == d for img in images)
+    # offsets checked by test/test_aad_decoder.c:95-184; versions come from the macros, not the struct
+    assert d[:4] == b"AAD\0" and d[4:8] == bytes([0, 0, 0, 4]) and d[8:12] == bytes([0, 0, 0, 18])
+    assert d[12:14] == bytes([0, 2]) and d[14:18] == bytes([1, 2, 3, 4]) and d[18:22] == (48000).to_bytes(4, "big")
+    assert d[22:24] == bytes([0, 3]) and d[24:26] == (1020).to_bytes(2, "big") and d[26:30] == (1316).to_bytes(4, "big")
+    assert d[30] == 1
+    for lib in libs:
+        hh = _valid_header()
+        data = np.zeros(64, dtype=np.uint8)
+        p8 = data.ctypes.data_as(C.POINTER(C.c_uint8))
+        assert lib.lib.AADEncoder_EncodeHeader(None, p8, 31) == INVALID_ARGUMENT
+        assert lib.lib.AADEncoder_EncodeHeader(C.byref(hh), None, 31) == INVALID_ARGUMENT
+        assert _encode_header(lib, hh, 30)[0] == INSUFFICIENT_DATA
+        for bad in HEADER_REJECTS:
+            if lib is not api and bad.get("num_channels") == 9:
+                bad = dict(num_channels=3)
+            rc, data = _encode_header(lib, _valid_header(**bad))
+            assert rc == INVALID_FORMAT, bad
+            assert not data.any(), "nothing may be written before validation passes"
+
+
+def test_decode_header_roundtrip_and_errors(product):
+    api, _ = product
+    h = _valid_header(num_channels=2, bits_per_sample=2, block_size=128, num_samples_per_block=188)
+    rc, data = _encode_header(api, h)
+    assert rc == OK
+    rc, got = api.decode_header(bytes(data[:31]))
+    assert rc == OK
+    want = h.as_dict()
+    want.update(format_version=capi.FORMAT_VERSION, codec_version=capi.CODEC_VERSION)
+    assert got.as_dict() == want
+    out = HeaderInfo()
+    p8 = data.ctypes.data_as(C.POINTER(C.c_uint8))
+    assert api.lib.AADDecoder_DecodeHeader(None, 31, C.byref(out)) == INVALID_ARGUMENT
+    assert api.lib.AADDecoder_DecodeHeader(p8, 31, None) == INVALID_ARGUMENT
+    assert api.lib.AADDecoder_DecodeHeader(p8, 30, C.byref(out)) == INSUFFICIENT_DATA
+    bad = bytearray(data[:31])
+    bad[0] = ord("a")
+    assert api.decode_header(bytes(bad))[0] == INVALID_FORMAT
+    # a parseable header with bad fields is accepted by DecodeHeader and rejected by SetHeader
+    dec = api.lib.AADDecoder_Create(None, 0)
+    assert dec
+    for off, width, value in [(4, 4, 0), (4, 4, 5), (8, 4, 0), (8, 4, 19), (12, 2, 0), (12, 2, 9), (14, 4, 0),
+                              (18, 4, 0), (22, 2, 0), (22, 2, 5), (24, 2, 0), (24, 2, 35), (26, 4, 0), (30, 1, 2)]:
+        img = bytearray(data[:31])
+        img[off:off + width] = value.to_bytes(width, "big")
+        rc, parsed = api.decode_header(bytes(img))
+        assert rc == OK
+        assert api.lib.AADDecoder_SetHeader(dec, C.byref(parsed)) == INVALID_FORMAT, (off, value)
+    img = bytearray(data[:31])
+    img[12:14] = (1).to_bytes(2, "big")
+    img[30] = capi.CH_MS
+    rc, parsed = api.decode_header(bytes(img))
+    assert rc == OK and api.lib.AADDecoder_SetHeader(dec, C.byref(parsed)) == INVALID_FORMAT
+    rc, parsed = api.decode_header(bytes(data[:31]))
+    assert api.lib.AADDecoder_SetHeader(dec, C.byref(parsed)) == OK
+    assert api.lib.AADDecoder_SetHeader(None, C.byref(parsed)) == INVALID_ARGUMENT
+    assert api.lib.AADDecoder_SetHeader(dec, None) == INVALID_ARGUMENT
+    api.lib.AADDecoder_Destroy(dec)
+
+
+def test_encoder_handle_lifecycle(product):
+    lib = product[0].lib
+    ws = lib.AADEncoder_CalculateWorkSize(1024)
+    assert ws > 0
+    assert lib.AADEncoder_CalculateWorkSize(0) == -1
+    work = C.create_string_buffer(ws)
+    enc = lib.AADEncoder_Create(1024, work, ws)
+    assert enc and C.addressof(work) <= enc < C.addressof(work) + 16
+    lib.AADEncoder_Destroy(enc)                       # caller memory: frees nothing
+    own = lib.AADEncoder_Create(1024, None, 0)
+    assert own
+    lib.AADEncoder_Destroy(own)
+    lib.AADEncoder_Destroy(None)
+    assert not lib.AADEncoder_Create(0, None, 0)
+    assert not lib.AADEncoder_Create(0, work, ws)
+    assert not lib.AADEncoder_Create(1024, None, ws)
+    assert not lib.AADEncoder_Create(1024, work, 0)
+    assert not lib.AADEncoder_Create(1024, work, ws - 1)
+
+
+def test_decoder_handle_lifecycle(product):
+    lib = product[0].lib
+    ws = lib.AADDecoder_CalculateWorkSize()
+    assert ws > 0
+    work = C.create_string_buffer(ws)
+    dec = lib.AADDecoder_Create(work, ws)
+    assert dec
+    lib.AADDecoder_Destroy(dec)
+    own = lib.AADDecoder_Create(None, 0)
+    assert own
+    lib.AADDecoder_Destroy(own)
+    assert not lib.AADDecoder_Create(None, ws)
+    assert not lib.AADDecoder_Create(work, 0)
+    assert not lib.AADDecoder_Create(work, ws - 1)
+
+
+def test_set_encode_parameter_and_call_order_errors(product):
+    api, _ = product
+    lib = api.lib
+    enc = lib.AADEncoder_Create(256, None, 0)
+    ok = make_param(1, 8000, 4, 256, False, 1)
+    assert lib.AADEncoder_SetEncodeParameter(None, C.byref(ok)) == INVALID_ARGUMENT
+    assert lib.AADEncoder_SetEncodeParameter(enc, None) == INVALID_ARGUMENT
+    for bad in (make_param(1, 8000, 0, 256), make_param(1, 8000, 5, 256), make_param(1, 8000, 4, 0),
+                make_param(1, 8000, 4, 17), make_param(0, 8000, 4, 256), make_param(9, 8000, 4, 1024)):
+        assert lib.AADEncoder_SetEncodeParameter(enc, C.byref(bad)) == INVALID_FORMAT
+    bad = make_param(1, 8000, 4, 256)
+    bad.ch_process_method = capi.CH_INVALID
+    assert lib.AADEncoder_SetEncodeParameter(enc, C.byref(bad)) == INVALID_FORMAT
+    # EncodeWhole before SetEncodeParameter, and NULL arguments (src/aad_encoder.c:826-834)
+    pcm = np.zeros((1, 64), dtype=np.int32)
+    out = np.zeros(4096, dtype=np.uint8)
+    size = C.c_uint32()
+    rows = capi._planar_pointers([pcm[0]])
+    p8 = out.ctypes.data_as(C.POINTER(C.c_uint8))
+    assert lib.AADEncoder_EncodeWhole(enc, rows, 64, p8, 4096, C.byref(size)) == capi.PARAMETER_NOT_SET
+    assert lib.AADEncoder_SetEncodeParameter(enc, C.byref(ok)) == OK
+    assert lib.AADEncoder_EncodeWhole(None, rows, 64, p8, 4096, C.byref(size)) == INVALID_ARGUMENT
+    assert lib.AADEncoder_EncodeWhole(enc, None, 64, p8, 4096, C.byref(size)) == INVALID_ARGUMENT
+    assert lib.AADEncoder_EncodeWhole(enc, rows, 64, None, 4096, C.byref(size)) == INVALID_ARGUMENT
+    assert lib.AADEncoder_EncodeWhole(enc, rows, 64, p8, 4096, None) == INVALID_ARGUMENT
+    # header problems surface before any device work: too small a buffer, zero samples
+    assert lib.AADEncoder_EncodeWhole(enc, rows, 64, p8, 30, C.byref(size)) == INSUFFICIENT_DATA
+    assert lib.AADEncoder_EncodeWhole(enc, rows, 0, p8, 4096, C.byref(size)) == INVALID_FORMAT
+    lib.AADEncoder_Destroy(enc)
+    # decoder: DecodeBlock before SetHeader, NULLs
+    dec = lib.AADDecoder_Create(None, 0)
+    n = C.c_uint32()
+    assert lib.AADDecoder_DecodeBlock(dec, p8, 64, rows, 1, 64, C.byref(n)) == capi.PARAMETER_NOT_SET
+    assert lib.AADDecoder_DecodeBlock(None, p8, 64, rows, 1, 64, C.byref(n)) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeBlock(dec, None, 64, rows, 1, 64, C.byref(n)) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeBlock(dec, p8, 64, None, 1, 64, C.byref(n)) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeBlock(dec, p8, 64, rows, 1, 64, None) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeWhole(None, p8, 64, rows, 1, 64) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeWhole(dec, None, 64, rows, 1, 64) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeWhole(dec, p8, 64, None, 1, 64) == INVALID_ARGUMENT
+    assert lib.AADDecoder_DecodeWhole(dec, p8, 10, rows, 1, 64) == INSUFFICIENT_DATA
+    assert lib.AADDecoder_DecodeWhole(dec, p8, 64, rows, 1, 64) == INVALID_FORMAT      # no "AAD\0" signature
+    # a valid header with too small a PCM buffer (src/aad_decoder.c:506-509)
+    rc, img = _encode_header(api, _valid_header(num_channels=2, block_size=64, num_samples_per_block=32))
+    p_img = img.ctypes.data_as(C.POINTER(C.c_uint8))
+    rows2 = capi._planar_pointers([np.zeros(2048, dtype=np.int32), np.zeros(2048, dtype=np.int32)])
+    assert lib.AADDecoder_DecodeWhole(dec, p_img, 64, rows2, 1, 2048) == capi.INSUFFICIENT_BUFFER
+    assert lib.AADDecoder_DecodeWhole(dec, p_img, 64, rows2, 2, 1023) == capi.INSUFFICIENT_BUFFER
+    lib.AADDecoder_Destroy(dec)
+
+
+def test_no_cpu_fallback_without_a_device(product):
+    """On a box without CUDA the compute entry points must fail loudly, not compute on the CPU."""
+    api, gpu = product
+    if gpu.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(Exception):
+        gpu.create(0)
+    assert "no CPU fallback" in gpu.last_error() or gpu.last_error()
+    pcm = np.zeros((1, 64), dtype=np.int32)
+    rc, data = api.encode_whole(pcm, 8000, 4)
+    assert rc == capi.NG and data == b""
+
+
+def test_stream_size_helpers(product, oracle):
+    _, gpu = product
+    import aadtest
+    for ch, bits, block, n in [(1, 4, 1024, 441000), (2, 3, 1024, 5000), (2, 2, 256, 4), (1, 3, 64, 125), (8, 3, 1024, 3000)]:
+        prm = make_param(ch, 44100, bits, block)
+        pcm = aadtest.signal("music", ch, n, 3)
+        rc, data = oracle.encode(pcm, 44100, bits, block, False, 0)
+        assert rc == 0
+        assert gpu.stream_bytes(prm, n) == len(data)
+        assert gpu.stream_bytes_bound(prm, n) >= len(data)
+
+
+def test_synth_generator_mirror_is_deterministic(product):
+    _, gpu = product
+    from aad_b200.synth import synth_pcm16
+    lut = gpu.synth_lut()
+    assert lut[0] == 0 and lut[256] == 32767 and lut[768] == -32767
+    a = synth_pcm16(lut, 5, 2, 2, 1000, 44100)
+    b = synth_pcm16(lut, 6, 1, 2, 1000, 44100)
+    assert np.array_equal(a[1], b[0]) and not np.array_equal(a[0], a[1])
+    assert a.dtype == np.int16 and abs(int(a.max())) > 10000
