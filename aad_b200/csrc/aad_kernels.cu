@@ -26,6 +26,7 @@ __device__ const int16_t g_delta3[4] = AADK_DELTA3_INIT;
 __device__ const int16_t g_delta4[8] = AADK_DELTA4_INIT;
 
 unsigned long long g_launches = 0;
+int g_force_generic = 0;   /* tests: route everything through the generic kernels */
 
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -436,9 +437,12 @@ inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((
 
 }  // namespace
 
+#include "aad_encode_fast.cuh"
+
 extern "C" {
 
 uint64_t aadk_launch_count(void) { return g_launches; }
+void aadk_force_generic(int on) { g_force_generic = on; }
 
 int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
 {
@@ -467,6 +471,17 @@ int aadk_launch_encode(const struct aadk_encode_params *p, void *stream)
   cudaStream_t s = (cudaStream_t)stream;
   const uint64_t threads = (uint64_t)p->num_streams * p->geo.channels;
   if (threads == 0 || p->block_end <= p->block_begin) return 0;
+  if (enc_fast_eligible(*p) && !g_force_generic) {
+    int rc;
+    switch (p->geo.bits) {
+      case 4: rc = enc_fast_launch<4>(*p, s); break;
+      case 3: rc = enc_fast_launch<3>(*p, s); break;
+      case 2: rc = enc_fast_launch<2>(*p, s); break;
+      default: return (int)cudaErrorInvalidValue;
+    }
+    g_launches++;
+    return rc;
+  }
   const unsigned block = 128, grid = grid_for(threads, block);
   switch (p->geo.bits) {
     case 4: aad_encode_generic<4><<<grid, block, 0, s>>>(*p); break;

@@ -82,6 +82,8 @@ int aadk_launch_interleave16(const int16_t *planar, uint64_t ch_stride, int16_t 
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t aadk_launch_count(void);
+/* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths */
+void aadk_force_generic(int on);
 
 #ifdef __cplusplus
 }
