@@ -1,0 +1,376 @@
+/*
+ * aad_decode_fast.cuh -- the production decoder kernel (included by aad_kernels.cu).
+ *
+ * One thread = one (block, channel) chain (every block header reloads the whole chain state,
+ * src/aad_decoder.c:364-380).  A warp owns 32/C consecutive blocks of one stream and walks them
+ * in windows of 128 samples per chain:
+ *
+ *   global .aad  --16-byte coalesced loads (aligned superset, prefetched one window ahead)-->
+ *   shared input rows --per-lane word reads + funnel shift (any byte alignment)--> sample chain
+ *   --8-byte stores--> shared output rows --coalesced 8-byte row stores--> global PCM
+ *
+ * so no global access is ever lane-strided (the generic kernel's byte loads / 2-byte stores touch
+ * 32 lines per instruction).  Windows are cut on input bytes (TB = 16*bits*C per block), chosen so
+ * that a window never splits a code group and the block header (18*C bytes) plus, for mono, one
+ * half step bring the read pointer back to word alignment.
+ *
+ * Tables: step size as uint16 indexed directly by the Q4 step index (the chain keeps 2*index =
+ * the byte offset), index delta replicated per lane; both in shared memory.
+ */
+#pragma once
+
+namespace {
+
+constexpr int kDecWarps = 4;
+constexpr int kDecWindow = 128;           /* samples per chain per window */
+constexpr int kDecOutPitch = 264;         /* 256 + 8: conflict-free 8-byte shared accesses */
+
+struct DecTables {
+  uint16_t step[kEncLutEntries + 7];      /* step[stepsize_index] */
+  int delta2[8][32];                      /* 2 * index delta per magnitude code, one column per lane */
+};
+
+template <int BITS, int C>
+struct DecGeom {
+  static constexpr int GB = (BITS == 3) ? 3 : 1;
+  static constexpr int TB = 16 * BITS * C;                 /* input bytes per block per window */
+  static constexpr int IN_CHUNKS = TB / 16 + 1;            /* aligned superset */
+  static constexpr int IN_PITCH = 16 * IN_CHUNKS;
+  static constexpr int IN_ROWS = 32 / C;
+  static constexpr int IN_LOADS = (IN_ROWS * IN_CHUNKS + 31) / 32;
+  static constexpr int IN_BYTES = IN_ROWS * IN_PITCH + 16; /* + slack for the funnel look-ahead word */
+  static constexpr int STEP_BYTES = (BITS == 3) ? 12 : 4;
+  static constexpr int SPS = STEP_BYTES * 8 / (BITS * C);  /* samples per chain per step */
+  static constexpr int HALF_BYTES = STEP_BYTES / 2;        /* mono only: 18-byte header -> word alignment */
+  static constexpr int WARP_BYTES = ((IN_BYTES + 15) & ~15) + 32 * kDecOutPitch;
+};
+
+template <int BITS>
+__device__ __forceinline__ void dec_load_tables(DecTables &t)
+{
+  for (int i = threadIdx.x; i < kEncLutEntries; i += blockDim.x) t.step[i] = g_step_table[(i + 8) >> 4];
+  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+    const int k = i >> 5;
+    int d = 0;
+    if (BITS == 4) d = g_delta4[k];
+    if (BITS == 3) d = g_delta3[k & 3];
+    if (BITS == 2) d = g_delta2[k & 1];
+    t.delta2[k][i & 31] = 2 * d;
+  }
+  __syncthreads();
+}
+
+struct DecChain {
+  int32_t h0, h1, h2, h3;
+  int32_t w0, w1, w2, w3;
+  int32_t idx2;   /* 2 * stepsize_index = byte offset into DecTables::step */
+};
+
+/* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
+template <int BITS, int POS>
+__device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t, const int *dl)
+{
+  constexpr uint32_t kMag2Mask = (1u << BITS) - 2u;          /* 2 * magnitude */
+  const int32_t step = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(t.step) + c.idx2);
+  const uint32_t u = ((POS >= 1) ? (v >> (POS >= 1 ? POS - 1 : 0)) : (v << 1)) & kMag2Mask;
+  const bool neg = (v & (1u << (POS + BITS - 1))) != 0u;
+  const int32_t qa = (int32_t)(step * u + step) >> (BITS - 1);   /* step * (2*mag + 1) */
+  const int32_t q = neg ? -qa : qa;
+  const uint32_t acc = (1u << 14) + (uint32_t)c.h0 * (uint32_t)c.w0 + (uint32_t)c.h1 * (uint32_t)c.w1 +
+                       (uint32_t)c.h2 * (uint32_t)c.w2 + (uint32_t)c.h3 * (uint32_t)c.w3;
+  const int32_t p = (int32_t)acc >> 15;
+  const int32_t r = max(__viaddmin_s32(q, p, 32767), -32768);
+  c.idx2 = __viaddmin_s32_relu(c.idx2, dl[u * 16], 2 * AADF_INDEX_MAX);   /* dl[mag * 32] */
+  c.w0 += (int32_t)((uint32_t)q * (uint32_t)c.h0 + (1u << 14)) >> 18;
+  c.w1 += (int32_t)((uint32_t)q * (uint32_t)c.h1 + (1u << 14)) >> 18;
+  c.w2 += (int32_t)((uint32_t)q * (uint32_t)c.h2 + (1u << 14)) >> 18;
+  c.w3 += (int32_t)((uint32_t)q * (uint32_t)c.h3 + (1u << 14)) >> 18;
+  c.h3 = c.h2;
+  c.h2 = c.h1;
+  c.h1 = c.h0;
+  c.h0 = r;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t dec_pack2(int32_t a, int32_t b) { return __byte_perm((uint32_t)a, (uint32_t)b, 0x5410); }
+
+/* All codes of one byte (4-bit: 2, 2-bit: 4), byte at bits [8*K, 8*K+8) of v; samples appended to o[]. */
+template <int BITS, int K>
+__device__ __forceinline__ void dec_byte(DecChain &c, uint32_t v, const DecTables &t, const int *dl, int32_t *o)
+{
+  if (BITS == 4) {
+    o[0] = dec_sample<4, 8 * K + 4>(c, v, t, dl);
+    o[1] = dec_sample<4, 8 * K>(c, v, t, dl);
+  } else {
+    o[0] = dec_sample<2, 8 * K + 6>(c, v, t, dl);
+    o[1] = dec_sample<2, 8 * K + 4>(c, v, t, dl);
+    o[2] = dec_sample<2, 8 * K + 2>(c, v, t, dl);
+    o[3] = dec_sample<2, 8 * K>(c, v, t, dl);
+  }
+}
+
+/* the 8 codes of one 3-bit group held big-endian in the low 24 bits of g */
+__device__ __forceinline__ void dec_group3(DecChain &c, uint32_t g, const DecTables &t, const int *dl, int32_t *o)
+{
+  o[0] = dec_sample<3, 21>(c, g, t, dl);
+  o[1] = dec_sample<3, 18>(c, g, t, dl);
+  o[2] = dec_sample<3, 15>(c, g, t, dl);
+  o[3] = dec_sample<3, 12>(c, g, t, dl);
+  o[4] = dec_sample<3, 9>(c, g, t, dl);
+  o[5] = dec_sample<3, 6>(c, g, t, dl);
+  o[6] = dec_sample<3, 3>(c, g, t, dl);
+  o[7] = dec_sample<3, 0>(c, g, t, dl);
+}
+
+/* store N (multiple of 4) samples to the lane's shared output row at sample offset `at` */
+template <int N>
+__device__ __forceinline__ void dec_emit(unsigned char *orow, uint32_t at, const int32_t *o)
+{
+#pragma unroll
+  for (int k = 0; k < N; k += 4)
+    *reinterpret_cast<uint2 *>(orow + 2 * (at + k)) = make_uint2(dec_pack2(o[k], o[k + 1]), dec_pack2(o[k + 2], o[k + 3]));
+}
+
+template <int BITS, int C>
+__global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_decode_params p)
+{
+  using G = DecGeom<BITS, C>;
+  extern __shared__ __align__(16) unsigned char dec_smem[];
+  DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
+  dec_load_tables<BITS>(tab);
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * G::WARP_BYTES;
+  unsigned char *out_rows = in_rows + ((G::IN_BYTES + 15) & ~15);
+  const int *dl = &tab.delta2[0][lane];
+
+  const uint32_t spb = p.geo.samples_per_block;
+  const uint32_t bs = p.geo.block_size;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint32_t warps_per_stream = (nblocks + G::IN_ROWS - 1) / G::IN_ROWS;
+  const uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp;
+  const uint64_t stream = gw / warps_per_stream;
+  if (stream >= p.num_streams) return;                      /* whole warp */
+  const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * G::IN_ROWS;
+
+  const uint8_t *slot = p.aad + stream * p.aad_stride;
+  const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
+  uint32_t ns = p.uniform_samples;
+  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+
+  /* this lane's chain */
+  const uint32_t row = lane / C, ch = lane % C;
+  const uint32_t b = b0 + row;
+  const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+  const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
+  const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;   /* samples this chain delivers */
+  int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+
+  /* loader role: IN_LOADS 16-byte chunks per lane per window */
+  const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
+  const uint8_t *ld_ptr[G::IN_LOADS];
+  uint32_t ld_smem[G::IN_LOADS];
+#pragma unroll
+  for (int m = 0; m < G::IN_LOADS; m++) {
+    const uint32_t f = lane + 32u * m;
+    const uint32_t rr = f / G::IN_CHUNKS, cc = f % G::IN_CHUNKS;
+    const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
+    ld_ptr[m] = (f < (uint32_t)(G::IN_ROWS * G::IN_CHUNKS)) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
+    ld_smem[m] = rr * G::IN_PITCH + 16u * cc;
+  }
+  const uint8_t *slot_end = slot + size;
+  auto fetch = [&](int m) -> uint4 {
+    const uint8_t *q = ld_ptr[m];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (q == nullptr || q >= slot_end) return v;
+    if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
+    unsigned char tmp[16];                      /* the chunk that straddles the end of the data: */
+#pragma unroll
+    for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past it read as zero */
+    v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
+    v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
+    v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
+    v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+    return v;
+  };
+
+  /* reader role: this lane's block row in shared memory */
+  const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
+  const unsigned char *irow = in_rows + row * G::IN_PITCH;
+  unsigned char *orow = out_rows + lane * kDecOutPitch;
+  auto in_u8 = [&](uint32_t pos) -> uint32_t { return irow[a_r + pos]; };
+
+  DecChain c;
+  c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+
+  const uint32_t windows = (bs + G::TB - 1) / G::TB;
+  uint4 pre[G::IN_LOADS];
+#pragma unroll
+  for (int m = 0; m < G::IN_LOADS; m++) pre[m] = fetch(m);
+
+  uint32_t out_base = 0;                                   /* first output sample of this window */
+  for (uint32_t w = 0; w < windows; w++) {
+    /* stage this window, start the next one */
+#pragma unroll
+    for (int m = 0; m < G::IN_LOADS; m++)
+      if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
+    __syncwarp();
+    if (w + 1 < windows) {
+#pragma unroll
+      for (int m = 0; m < G::IN_LOADS; m++) {
+        if (ld_ptr[m] != nullptr) ld_ptr[m] += G::TB;
+        pre[m] = fetch(m);
+      }
+    }
+
+    uint32_t produced = 0;      /* samples this chain wrote into its output row in this window */
+    uint32_t pos = 0;           /* byte position inside the window */
+    if (w == 0) {
+      /* block header, src/aad_decoder.c:364-380: u16 (index << 4 | shift), 4 x (u16 weight, u16 history) */
+      const uint32_t hp = AADF_CHANNEL_HEADER_BYTES * ch;
+      const uint32_t head = (in_u8(hp) << 8) | in_u8(hp + 1);
+      c.idx2 = 2 * (int32_t)(int16_t)(head >> 4);
+      c.idx2 = max(0, min(c.idx2, 2 * AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
+      const uint32_t shift = head & 0xFu;
+      int32_t wv[4], hv[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)((in_u8(hp + 2 + 4 * k) << 8) | in_u8(hp + 3 + 4 * k)) << shift);
+        hv[k] = (int32_t)(int16_t)((in_u8(hp + 4 + 4 * k) << 8) | in_u8(hp + 5 + 4 * k));
+      }
+      c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
+      c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
+      const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };   /* src/aad_decoder.c:386-391 */
+      dec_emit<4>(orow, 0, first4);
+      produced = 4;
+      pos = AADF_CHANNEL_HEADER_BYTES * C;
+      if (C == 1) {
+        /* half a step: the 18-byte header leaves the row 2 bytes off word alignment */
+        if (BITS == 3) {
+          int32_t o[16];
+          dec_group3(c, (in_u8(pos) << 16) | (in_u8(pos + 1) << 8) | in_u8(pos + 2), tab, dl, o);
+          dec_group3(c, (in_u8(pos + 3) << 16) | (in_u8(pos + 4) << 8) | in_u8(pos + 5), tab, dl, o + 8);
+          dec_emit<16>(orow, produced, o);
+          produced += 16;
+        } else {
+          const uint32_t v = in_u8(pos) | (in_u8(pos + 1) << 8);
+          int32_t o[2 * (BITS == 4 ? 2 : 4)];
+          dec_byte<BITS, 0>(c, v, tab, dl, o);
+          dec_byte<BITS, 1>(c, v, tab, dl, o + (BITS == 4 ? 2 : 4));
+          dec_emit<2 * (BITS == 4 ? 2 : 4)>(orow, produced, o);
+          produced += 2 * (BITS == 4 ? 2 : 4);
+        }
+        pos += G::HALF_BYTES;
+      }
+    }
+
+    /* whole steps: sliding 32-bit words + funnel shift, any byte alignment */
+    {
+      const uint32_t at = a_r + pos;
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow + (at & ~3u));
+      const uint32_t sh = (at & 3u) * 8u;
+      uint32_t lo = *wp++;
+      const uint32_t steps = (G::TB - pos) / G::STEP_BYTES;
+      for (uint32_t s = 0; s < steps; s++) {
+        if (BITS == 3) {
+          uint32_t x[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const uint32_t hi = *wp++;
+            x[k] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+          }
+          int32_t o[G::SPS];
+          if (C == 1) {
+            dec_group3(c, __byte_perm(x[0], 0u, 0x4012), tab, dl, o);
+            dec_group3(c, __byte_perm(x[0], x[1], 0x4345), tab, dl, o + 8);
+            dec_group3(c, __byte_perm(x[1], x[2], 0x4234), tab, dl, o + 16);
+            dec_group3(c, __byte_perm(x[2], 0u, 0x4123), tab, dl, o + 24);
+          } else {   /* two channels: groups alternate, 3 bytes each */
+            const uint32_t sel_a = ch ? 0x0345u : 0x0012u, sel_b = ch ? 0x0567u : 0x0234u;
+            dec_group3(c, __byte_perm(x[0], x[1], sel_a), tab, dl, o);
+            dec_group3(c, __byte_perm(x[1], x[2], sel_b), tab, dl, o + 8);
+          }
+          dec_emit<G::SPS>(orow, produced, o);
+        } else {
+          const uint32_t hi = *wp++;
+          uint32_t v = __funnelshift_r(lo, hi, sh);
+          lo = hi;
+          constexpr int PER_BYTE = (BITS == 4) ? 2 : 4;
+          int32_t o[G::SPS];
+          if (C == 1) {
+            dec_byte<BITS, 0>(c, v, tab, dl, o);
+            dec_byte<BITS, 1>(c, v, tab, dl, o + PER_BYTE);
+            dec_byte<BITS, 2>(c, v, tab, dl, o + 2 * PER_BYTE);
+            dec_byte<BITS, 3>(c, v, tab, dl, o + 3 * PER_BYTE);
+          } else {   /* two channels: bytes alternate */
+            v >>= 8u * ch;
+            dec_byte<BITS, 0>(c, v, tab, dl, o);
+            dec_byte<BITS, 2>(c, v, tab, dl, o + PER_BYTE);
+          }
+          dec_emit<G::SPS>(orow, produced, o);
+        }
+        produced += G::SPS;
+      }
+    }
+    __syncwarp();
+
+    /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
+    for (uint32_t rr = 0; rr < 32; rr++) {
+      const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+      const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+      const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+      if (n_rr <= out_base) continue;                       /* uniform */
+      const uint32_t count = min(made, n_rr - out_base);
+      int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+      const unsigned char *srow = out_rows + rr * kDecOutPitch;
+      const uint32_t s0 = lane * 4u;
+      if (s0 + 4u <= count) {
+        *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+      } else {
+        for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+      }
+    }
+    out_base += produced;       /* identical in every lane */
+    __syncwarp();
+  }
+}
+
+inline bool dec_fast_eligible(const aadk_decode_params &p)
+{
+  if (p.out32) return false;
+  if (p.geo.channels != 1 && p.geo.channels != 2) return false;
+  if (p.geo.samples_per_block % 4u) return false;
+  if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u)) return false;
+  /* the window arithmetic assumes the canonical block layout: header, then whole groups */
+  const uint32_t gs = aadf_group_samples(p.geo.bits), gb = aadf_group_bytes(p.geo.bits);
+  if (p.geo.samples_per_block < AADF_TAPS || (p.geo.samples_per_block - AADF_TAPS) % gs) return false;
+  if (p.geo.block_size != p.geo.channels * (AADF_CHANNEL_HEADER_BYTES + (p.geo.samples_per_block - AADF_TAPS) / gs * gb))
+    return false;
+  return true;
+}
+
+template <int BITS, int C>
+int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
+{
+  using G = DecGeom<BITS, C>;
+  const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * G::WARP_BYTES;
+  /* per device, so not cached in a static: a process may drive several GPUs */
+  cudaError_t e = cudaFuncSetAttribute(aad_decode_fast<BITS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
+  const unsigned grid = (unsigned)((warps + kDecWarps - 1) / kDecWarps);
+  aad_decode_fast<BITS, C><<<grid, kDecWarps * 32, smem, s>>>(p);
+  return (int)cudaGetLastError();
+}
+
+template <int BITS>
+int dec_fast_launch(const aadk_decode_params &p, cudaStream_t s)
+{
+  return p.geo.channels == 1 ? dec_fast_launch_bc<BITS, 1>(p, s) : dec_fast_launch_bc<BITS, 2>(p, s);
+}
+
+}  // namespace

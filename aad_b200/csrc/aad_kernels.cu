@@ -438,6 +438,7 @@ inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((
 }  // namespace
 
 #include "aad_encode_fast.cuh"
+#include "aad_decode_fast.cuh"
 
 extern "C" {
 
@@ -450,12 +451,23 @@ int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
   if (p->block_end <= p->block_begin) return 0;
   const uint64_t threads = (uint64_t)p->num_streams * (p->block_end - p->block_begin) * p->geo.channels;
   if (threads == 0) return 0;
-  const unsigned block = 128, grid = grid_for(threads, block);
-  switch (p->geo.bits) {
-    case 4: aad_decode_generic<4><<<grid, block, 0, s>>>(*p); break;
-    case 3: aad_decode_generic<3><<<grid, block, 0, s>>>(*p); break;
-    case 2: aad_decode_generic<2><<<grid, block, 0, s>>>(*p); break;
-    default: return (int)cudaErrorInvalidValue;
+  if (dec_fast_eligible(*p) && !g_force_generic) {
+    int rc;
+    switch (p->geo.bits) {
+      case 4: rc = dec_fast_launch<4>(*p, s); break;
+      case 3: rc = dec_fast_launch<3>(*p, s); break;
+      case 2: rc = dec_fast_launch<2>(*p, s); break;
+      default: return (int)cudaErrorInvalidValue;
+    }
+    if (rc != 0) return rc;
+  } else {
+    const unsigned block = 128, grid = grid_for(threads, block);
+    switch (p->geo.bits) {
+      case 4: aad_decode_generic<4><<<grid, block, 0, s>>>(*p); break;
+      case 3: aad_decode_generic<3><<<grid, block, 0, s>>>(*p); break;
+      case 2: aad_decode_generic<2><<<grid, block, 0, s>>>(*p); break;
+      default: return (int)cudaErrorInvalidValue;
+    }
   }
   g_launches++;
   if (p->geo.ms && p->geo.channels >= 2) {

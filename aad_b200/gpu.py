@@ -33,7 +33,7 @@ class GpuApi:
         "AADGpu_SetMaxChannels", "AADGpu_GetMaxChannels", "AADGpu_HostAlloc", "AADGpu_HostFree",
         "AADGpu_StreamBytesBound", "AADGpu_StreamBytes", "AADGpu_EncodeBatchDevice", "AADGpu_DecodeBatchDevice",
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
-        "AADGpu_Interleave16Device", "AADGpu_SynthLut",
+        "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath",
     )
 
     def __init__(self, lib):
@@ -60,6 +60,7 @@ class GpuApi:
             "AADGpu_Deinterleave16Device": (C.c_int, [vp, vp, vp, u64, u32, u32, vp]),
             "AADGpu_Interleave16Device": (C.c_int, [vp, vp, u64, vp, u32, u32, vp]),
             "AADGpu_SynthLut": (None, [vp]),
+            "AADGpu_SetKernelPath": (None, [C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)

@@ -49,6 +49,9 @@ const char *AADGpu_LastError(void);                      /* thread-local, never 
 uint64_t AADGpu_KernelLaunchCount(void);                 /* kernels launched by this library so far */
 void AADGpu_SetMaxChannels(uint32_t max_channels);       /* 2 = stock reference limit, 8 = default */
 uint32_t AADGpu_GetMaxChannels(void);
+/* 0 (default): fast kernels wherever the shape allows, generic kernels otherwise; 1: always the
+ * generic (any channel count / alignment) kernels.  Both are bit-exact; this exists for testing. */
+void AADGpu_SetKernelPath(int generic_only);
 
 /* pinned host memory for the host entry points (plain malloc'd memory works too, slower) */
 void *AADGpu_HostAlloc(size_t bytes);
@@ -84,6 +87,8 @@ AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
 /* ---- deterministic synthetic PCM (bench / tests), SURVEY.md 8(d) ------------------------ */
 AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                      uint32_t first_stream, int16_t *pcm_dev, void *stream);
+/* the generator's 1024-entry sine table (host arithmetic), so a host mirror can reproduce the batch */
+void AADGpu_SynthLut(int16_t lut[1024]);
 
 /* ---- WAV-order helpers on the device (src/main.c:122-126,175-179) ----------------------- */
 AADApiResult AADGpu_Deinterleave16Device(struct AADGpu *gpu, const int16_t *interleaved_dev, int16_t *planar_dev,

@@ -51,6 +51,55 @@ def test_golden_table_through_dropin_api(product, gpu_ctx):
         assert rc == OK and aadtest.pcm_sha(dec.astype(np.int16)) == case["pcm_sha"], case
 
 
+@pytest.mark.parametrize("generic_only", [0, 1])
+def test_golden_table_through_batch_api(product, gpu_ctx, generic_only):
+    """int16 batch entry points (the fast kernels when generic_only == 0), one stream per call and
+    all same-shaped cases of a source in one call."""
+    _, gpu = product
+    gpu.lib.AADGpu_SetKernelPath(generic_only)
+    try:
+        for case in aadtest.golden_table():
+            pcm, rate = _case_pcm(case)
+            aad, sizes = gpu.encode_batch(gpu_ctx, pcm[None], rate, case["bits"], case["max_block"], case["ms"], case["trials"])
+            data = aad[0, :sizes[0]].tobytes()
+            assert len(data) == case["aad_size"] and aadtest.sha(data) == case["aad_sha"], case
+            dec = gpu.decode_batch(gpu_ctx, aad, pcm.shape[1], rate, pcm.shape[0], case["bits"], case["max_block"],
+                                   case["ms"], sizes=sizes)
+            assert aadtest.pcm_sha(dec[0]) == case["pcm_sha"], case
+    finally:
+        gpu.lib.AADGpu_SetKernelPath(0)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_fast_and_generic_kernels_agree(product, gpu_ctx, bits, channels):
+    """Odd block sizes, odd lengths, many blocks per stream: fast path vs generic path, byte for byte."""
+    _, gpu = product
+    rng = np.random.default_rng(bits + 10 * channels)
+    for block in (64 * channels, 256, 1024, 4096):
+        n_streams, n_max = 70, 9000
+        lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+        lens[0] = n_max
+        pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+        for i in range(n_streams):
+            pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], channels, int(lens[i]), 50 + i)
+        res = []
+        for generic_only in (0, 1):
+            gpu.lib.AADGpu_SetKernelPath(generic_only)
+            try:
+                aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 48000, bits, block, channels == 2, 1, num_samples=lens)
+                dec = gpu.decode_batch(gpu_ctx, aad, n_max, 48000, channels, bits, block, channels == 2, sizes=sizes)
+            finally:
+                gpu.lib.AADGpu_SetKernelPath(0)
+            for i in range(n_streams):            # bytes past each stream's end are not part of the result
+                aad[i, sizes[i]:] = 0
+                dec[i, :, lens[i]:] = 0
+            res.append((aad, sizes, dec))
+        assert np.array_equal(res[0][1], res[1][1]), (bits, channels, block)
+        assert np.array_equal(res[0][0], res[1][0]), (bits, channels, block)
+        assert np.array_equal(res[0][2], res[1][2]), (bits, channels, block)
+
+
 def test_five_bits_is_rejected_like_the_reference(product, gpu_ctx):
     api, gpu = product
     pcm = aadtest.signal("sine", 1, 500)
