@@ -204,6 +204,34 @@ __device__ __forceinline__ double enc_trial_pass(EncChain &c, const EncSource<MS
   return sqrt((double)sum / (double)n);
 }
 
+/* Per-lane output stream for the mono case, where a chain's code bytes are contiguous: bytes are
+ * collected in a 64-bit register and leave as aligned 4-byte stores (single bytes only up to the
+ * first 4-byte boundary and for the last partial word): one store per 8 samples instead of four
+ * lane-strided byte stores. */
+struct EncByteStream {
+  uint8_t *ptr;          /* next byte to write */
+  unsigned long long acc;
+  uint32_t cnt;          /* bytes held in acc */
+  __device__ __forceinline__ void begin(uint8_t *p) { ptr = p; acc = 0ull; cnt = 0u; }
+  __device__ __forceinline__ void put(uint32_t value, uint32_t nbytes)   /* value: first byte in bits 0-7 */
+  {
+    acc |= (unsigned long long)value << (8u * cnt);
+    cnt += nbytes;
+    while (cnt >= 4u) {
+      if (((uintptr_t)ptr & 3u) == 0u) {
+        *reinterpret_cast<uint32_t *>(ptr) = (uint32_t)acc;
+        ptr += 4; acc >>= 32; cnt -= 4u;
+      } else {
+        *ptr++ = (uint8_t)acc; acc >>= 8; cnt -= 1u;
+      }
+    }
+  }
+  __device__ __forceinline__ void end()
+  {
+    while (cnt) { *ptr++ = (uint8_t)acc; acc >>= 8; cnt--; }
+  }
+};
+
 template <int BITS>
 __device__ __forceinline__ void enc_store_group(uint8_t *dp, uint32_t packed)
 {
@@ -311,6 +339,9 @@ __global__ void __launch_bounds__(128) aad_encode_fast(const aadk_encode_params 
     /* code groups, src/aad_encoder.c:661-722: full 16-sample units from prefetched vector loads ... */
     uint8_t *dp = blk + C * AADF_CHANNEL_HEADER_BYTES + ch * GB;
     const uint32_t gstride = C * GB;
+    const bool mono = (C == 1);                      /* uniform: contiguous code bytes -> word stores */
+    EncByteStream bytes;
+    bytes.begin(dp);
     uint32_t i = first + AADF_TAPS;
     const uint32_t units = (n > AADF_TAPS) ? (n - AADF_TAPS) / kEncUnit : 0;
     EncQuad<MS> cur[kEncUnitQuads], nxt[kEncUnitQuads];
@@ -323,15 +354,32 @@ __global__ void __launch_bounds__(128) aad_encode_fast(const aadk_encode_params 
 #pragma unroll
         for (int k = 0; k < kEncUnitQuads; k++) nxt[k].load(src, i + kEncUnit + 4 * k);
       }
-      uint32_t packed = 0;
+      /* the unit's codes, first sample in the most significant bits (16*BITS <= 64 bits) */
+      unsigned long long codes = 0ull;
 #pragma unroll
       for (int j = 0; j < kEncUnit; j++) {
         int32_t q;
-        packed = (packed << BITS) | enc_sample<BITS>(c, cur[j >> 2].get(src, j & 3), sh, q);
-        if ((j + 1) % GS == 0) {
+        codes = (codes << BITS) | enc_sample<BITS>(c, cur[j >> 2].get(src, j & 3), sh, q);
+      }
+      constexpr int kUnitBytes = kEncUnit * BITS / 8;          /* 8 / 6 / 4 */
+      if (mono) {
+        /* stream order = most significant byte first: byte-reverse, then feed little-endian */
+        const uint32_t hi = (uint32_t)(codes >> 32), lo = (uint32_t)codes;
+        if (BITS == 4) {
+          bytes.put(__byte_perm(hi, 0u, 0x0123), 4u);
+          bytes.put(__byte_perm(lo, 0u, 0x0123), 4u);
+        } else if (BITS == 3) {      /* 48 bits: bytes 5..0 of codes */
+          bytes.put(__byte_perm(hi, lo, 0x6701), 4u);   /* hi.b1, hi.b0, lo.b3, lo.b2 */
+          bytes.put(__byte_perm(lo, 0u, 0x4401), 2u);   /* lo.b1, lo.b0 */
+        } else {
+          bytes.put(__byte_perm(lo, 0u, 0x0123), 4u);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < kUnitBytes / (int)GB; g++) {
+          const uint32_t packed = (uint32_t)(codes >> (8 * GB * (kUnitBytes / GB - 1 - g))) & ((1u << (8 * GB)) - 1u);
           enc_store_group<BITS>(dp, packed);
           dp += gstride;
-          packed = 0;
         }
       }
 #pragma unroll
@@ -339,7 +387,7 @@ __global__ void __launch_bounds__(128) aad_encode_fast(const aadk_encode_params 
       i += kEncUnit;
     }
     /* ... then the tail in whole groups, zero padded past the end (src/aad_encoder.c:592-593) */
-    for (; i < limit; i += GS, dp += gstride) {
+    for (; i < limit; i += GS) {
       uint32_t packed = 0;
 #pragma unroll
       for (uint32_t j = 0; j < GS; j++) {
@@ -347,8 +395,15 @@ __global__ void __launch_bounds__(128) aad_encode_fast(const aadk_encode_params 
         const int32_t xs = (i + j < limit) ? src.at(i + j) : 0;
         packed = (packed << BITS) | enc_sample<BITS>(c, xs, sh, q);
       }
-      enc_store_group<BITS>(dp, packed);
+      if (mono) {
+        if (BITS == 3) bytes.put(__byte_perm(packed, 0u, 0x4012), 3u);
+        else bytes.put(packed, 1u);
+      } else {
+        enc_store_group<BITS>(dp, packed);
+        dp += gstride;
+      }
     }
+    if (mono) bytes.end();
   }
 
   if (p.state_out) {
