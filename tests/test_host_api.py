@@ -276,3 +276,23 @@ def test_synth_generator_mirror_is_deterministic(product):
     b = synth_pcm16(lut, 6, 1, 2, 1000, 44100)
     assert np.array_equal(a[1], b[0]) and not np.array_equal(a[0], a[1])
     assert a.dtype == np.int16 and abs(int(a.max())) > 10000
+
+
+def test_magic_division_tables_are_exact():
+    """The encoder's divide-free quantiser: umulhi(|d| << (b-1), M) >> L == (|d| << (b-2)) / step for
+    every table step and every reachable |d| (|sample - predict| < 2^17), all bit depths."""
+    import re
+    text = (ROOT / "aad_b200" / "csrc" / "aad_tables_data.h").read_text()
+
+    def table(name):
+        body = re.search(name + r" \{(.*?)\}", text.replace("\\\n", " "), re.S).group(1)
+        return [int(v.rstrip("u")) for v in re.findall(r"-?\d+u?", body)]
+
+    steps, magic, shift = table("AADK_STEP_TABLE_INIT"), table("AADK_STEP_MAGIC_INIT"), table("AADK_STEP_SHIFT_INIT")
+    assert len(steps) == len(magic) == len(shift) == 256
+    d = np.arange(0, 1 << 17, dtype=np.uint64)
+    for s, m, l in set(zip(steps, magic, shift)):
+        assert (1 << 31) <= m < (1 << 32) and l == (s - 1).bit_length()
+        for bits in (2, 3, 4):
+            fast = (((d << np.uint64(bits - 1)) * np.uint64(m)) >> np.uint64(32)) >> np.uint64(l)
+            assert np.array_equal(fast, (d << np.uint64(bits - 2)) // np.uint64(s)), (s, bits)
