@@ -10,7 +10,10 @@ library is missing, importing ``aad_b200.lib`` raises.
 from pathlib import Path
 
 PACKAGE_DIR = Path(__file__).resolve().parent
-LIBRARY_PATH = PACKAGE_DIR / "libaad_b200.so"
+import os as _os
+
+# AAD_B200_LIBRARY: load another build of the same library (kernel experiments); default = the in-tree build
+LIBRARY_PATH = Path(_os.environ.get("AAD_B200_LIBRARY") or PACKAGE_DIR / "libaad_b200.so")
 
 __all__ = ["PACKAGE_DIR", "LIBRARY_PATH", "load"]
 
