@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
   const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
   const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;   /* samples this chain delivers */
   int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+  int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;   /* row 0 of the warp */
+  const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb);
 
   /* loader role: IN_LOADS 16-byte chunks per lane per window */
   const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
@@ -318,19 +320,33 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     __syncwarp();
 
     /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
-    for (uint32_t rr = 0; rr < 32; rr++) {
-      const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
-      const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
-      const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
-      if (n_rr <= out_base) continue;                       /* uniform */
-      const uint32_t count = min(made, n_rr - out_base);
-      int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
-      const unsigned char *srow = out_rows + rr * kDecOutPitch;
-      const uint32_t s0 = lane * 4u;
-      if (s0 + 4u <= count) {
-        *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
-      } else {
-        for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+    if (all_full) {
+      /* every chain of the warp delivers a whole block: row addresses are plain arithmetic and the
+       * count is the same for every row -- `produced` (identical in every lane), clipped where the
+       * last window runs past the block; both are multiples of 4 */
+      if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+        const unsigned char *srow = out_rows + 8u * lane;
+        int16_t *dst = grow0 + out_base + 4u * lane;
+#pragma unroll
+        for (uint32_t rr = 0; rr < 32; rr++)
+          *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
+              *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+      }
+    } else {
+      for (uint32_t rr = 0; rr < 32; rr++) {
+        const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+        const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+        const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+        if (n_rr <= out_base) continue;                       /* uniform */
+        const uint32_t count = min(made, n_rr - out_base);
+        int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+        const unsigned char *srow = out_rows + rr * kDecOutPitch;
+        const uint32_t s0 = lane * 4u;
+        if (s0 + 4u <= count) {
+          *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+        } else {
+          for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+        }
       }
     }
     out_base += produced;       /* identical in every lane */
