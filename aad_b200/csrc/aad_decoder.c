@@ -110,6 +110,16 @@ static int geometry_is_consistent(const struct aadf_geometry *g)
   return (uint64_t)g->channels * (AADF_CHANNEL_HEADER_BYTES + groups * gb) <= g->block_size;
 }
 
+/* header checks for paths that do not go through a decoder handle (aad_gpu.c) */
+AADApiResult aaddec_check_header(const struct AADHeaderInfo *h)
+{
+  struct aadf_geometry geo;
+  if (h == NULL) return AAD_APIRESULT_INVALID_ARGUMENT;
+  if (!header_is_decodable(h)) return AAD_APIRESULT_INVALID_FORMAT;
+  geometry_of(h, &geo);
+  return geometry_is_consistent(&geo) ? AAD_APIRESULT_OK : AAD_APIRESULT_INVALID_FORMAT;
+}
+
 AADApiResult AADDecoder_DecodeBlock(struct AADDecoder *decoder, const uint8_t *data, uint32_t data_size,
                                     int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples,
                                     uint32_t *num_decode_samples)

@@ -11,6 +11,7 @@
  */
 #define _GNU_SOURCE
 #include "aad_gpu_internal.h"
+#include "aad_decoder.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -88,7 +89,7 @@ void AADGpu_Destroy(struct AADGpu *g)
   if (!g) return;
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
-  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut };
+  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut, &g->wav };
   for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
     if (bufs[i]->ptr) cudaFree(bufs[i]->ptr);
   for (int i = 0; i < 16; i++) {
@@ -601,5 +602,164 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
                          gpu->s_out), "D2H pcm");
   }
   CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  return AAD_APIRESULT_OK;
+}
+
+/* ---- WAV-order (interleaved int16) single-stream paths: what `aad -e / -d / -r` do ---------- */
+
+/* src/main.c:175-179 + AADEncoder_EncodeWhole, with the de-interleave done on the device: the
+ * samples of a 16-bit WAV data chunk go to HBM as they are.  Leaves the stream at gpu->aad + 1. */
+static AADApiResult encode_interleaved_device(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                              const struct aadf_geometry *geo, const int16_t *interleaved,
+                                              uint32_t num_samples, uint64_t *pitch_out, uint64_t *bytes_out)
+{
+  const uint32_t C = geo->channels;
+  const uint64_t pitch = round_up64(num_samples, 64);
+  const uint64_t bytes = aadf_stream_bytes(num_samples, C, geo->bits, geo->block_size, geo->samples_per_block);
+  const uint64_t bound = aadf_stream_bytes_bound(num_samples, geo->block_size, geo->samples_per_block);
+  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * num_samples * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
+  cudaStream_t s = gpu->s_run;
+  CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved, (size_t)C * num_samples * 2, cudaMemcpyHostToDevice, s), "H2D wav");
+  CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s),
+     "deinterleave kernel launch");
+  CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)bound + 128, s), "memset aad");
+  struct aadk_encode_params p;
+  memset(&p, 0, sizeof(p));
+  p.pcm = gpu->pcm.ptr;
+  p.pcm_clip_stride = (uint64_t)C * pitch;
+  p.pcm_ch_stride = pitch;
+  p.uniform_samples = num_samples;
+  p.num_streams = 1;
+  p.geo = *geo;
+  p.sampling_rate = prm->sampling_rate;
+  p.trials = prm->num_encode_trials;
+  p.aad = (uint8_t *)gpu->aad.ptr + 1;   /* block 0 lands 32-byte aligned */
+  p.aad_stride = bound;
+  p.block_begin = 0;
+  p.block_end = aadf_num_blocks(num_samples, geo->samples_per_block);
+  CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
+  *pitch_out = pitch;
+  *bytes_out = bytes;
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                        const int16_t *interleaved, uint32_t num_samples, uint8_t *data,
+                                        uint32_t data_size, uint32_t *output_size)
+{
+  if (!gpu || !prm || !interleaved || !data || !output_size) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (data_size < AADF_FILE_HEADER_BYTES) return AAD_APIRESULT_INSUFFICIENT_DATA;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  uint64_t pitch = 0, bytes = 0;
+  if (aadf_stream_bytes(num_samples, geo.channels, geo.bits, geo.block_size, geo.samples_per_block) > data_size)
+    return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  const AADApiResult e = encode_interleaved_device(gpu, prm, &geo, interleaved, num_samples, &pitch, &bytes);
+  if (e != AAD_APIRESULT_OK) return e;
+  CU(cudaMemcpyAsync(data, (uint8_t *)gpu->aad.ptr + 1, (size_t)bytes, cudaMemcpyDeviceToHost, gpu->s_run), "D2H aad");
+  CU(cudaStreamSynchronize(gpu->s_run), "sync");
+  *output_size = (uint32_t)bytes;
+  return AAD_APIRESULT_OK;
+}
+
+/* decode the stream at d_aad (device) into gpu->pcm (planar) and gpu->wav (interleaved) */
+static AADApiResult decode_to_interleaved_device(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *d_aad,
+                                                 uint64_t aad_bytes)
+{
+  struct aadf_geometry geo;
+  geo.channels = h->num_channels;
+  geo.bits = h->bits_per_sample;
+  geo.block_size = h->block_size;
+  geo.samples_per_block = h->num_samples_per_block;
+  geo.ms = (h->ch_process_method == AAD_CH_PROCESS_METHOD_MS) ? 1u : 0u;
+  const uint32_t C = geo.channels, ns = h->num_samples;
+  const uint64_t pitch = round_up64(ns, 64);
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * ns * 2)) return AAD_APIRESULT_NG;
+  cudaStream_t s = gpu->s_run;
+  /* samples of blocks the data does not reach stay zero (the reference leaves them untouched) */
+  CU(cudaMemsetAsync(gpu->pcm.ptr, 0, (size_t)C * pitch * 2, s), "memset pcm");
+  struct aadk_decode_params p;
+  memset(&p, 0, sizeof(p));
+  p.aad = d_aad;
+  p.aad_stride = aad_bytes;
+  p.uniform_size = (uint32_t)aad_bytes;
+  p.num_streams = 1;
+  p.geo = geo;
+  p.block_begin = 0;
+  p.block_end = aadf_num_blocks(ns, geo.samples_per_block);
+  p.uniform_samples = ns;
+  p.pcm = gpu->pcm.ptr;
+  p.pcm_clip_stride = (uint64_t)C * pitch;
+  p.pcm_ch_stride = pitch;
+  CU((cudaError_t)aadk_launch_decode(&p, s), "decode kernel launch");
+  CU((cudaError_t)aadk_launch_interleave16((const int16_t *)gpu->pcm.ptr, pitch, (int16_t *)gpu->wav.ptr, C, ns, s),
+     "interleave kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+/* the checks of AADDecoder_DecodeHeader + CheckHeaderFormat (src/aad_decoder.c:99-225), via the drop-in entry */
+static AADApiResult parse_stream_header(const uint8_t *data, uint32_t data_size, struct AADHeaderInfo *h)
+{
+  const AADApiResult r = AADDecoder_DecodeHeader(data, data_size, h);
+  if (r != AAD_APIRESULT_OK) return r;
+  return aaddec_check_header(h);
+}
+
+AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
+                                        int16_t *interleaved, uint32_t capacity_samples)
+{
+  if (!gpu || !data || !interleaved) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct AADHeaderInfo h;
+  const AADApiResult r = parse_stream_header(data, data_size, &h);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (capacity_samples < h.num_samples) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  uint64_t span = aadf_stream_bytes_bound(h.num_samples, h.block_size, h.num_samples_per_block);
+  if (span > data_size) span = data_size;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 128)) return AAD_APIRESULT_NG;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
+  CU(cudaMemcpyAsync(d_aad, data, (size_t)span, cudaMemcpyHostToDevice, gpu->s_run), "H2D aad");
+  const AADApiResult e = decode_to_interleaved_device(gpu, &h, d_aad, span);
+  if (e != AAD_APIRESULT_OK) return e;
+  CU(cudaMemcpyAsync(interleaved, gpu->wav.ptr, (size_t)h.num_channels * h.num_samples * 2, cudaMemcpyDeviceToHost, gpu->s_run),
+     "D2H wav");
+  CU(cudaStreamSynchronize(gpu->s_run), "sync");
+  return AAD_APIRESULT_OK;
+}
+
+/* src/main.c:275-346 (execute_reconstruction_core): encode, then decode what was encoded; the
+ * stream never leaves the device. */
+AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                             const int16_t *interleaved, uint32_t num_samples,
+                                             int16_t *reconstructed, uint32_t *encoded_size)
+{
+  if (!gpu || !prm || !interleaved || !reconstructed) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  uint64_t pitch = 0, bytes = 0;
+  AADApiResult e = encode_interleaved_device(gpu, prm, &geo, interleaved, num_samples, &pitch, &bytes);
+  if (e != AAD_APIRESULT_OK) return e;
+  struct AADHeaderInfo h;
+  memset(&h, 0, sizeof(h));
+  h.num_channels = (uint16_t)geo.channels;
+  h.num_samples = num_samples;
+  h.sampling_rate = prm->sampling_rate;
+  h.bits_per_sample = (uint16_t)geo.bits;
+  h.block_size = (uint16_t)geo.block_size;
+  h.num_samples_per_block = geo.samples_per_block;
+  h.ch_process_method = prm->ch_process_method;
+  e = decode_to_interleaved_device(gpu, &h, (const uint8_t *)gpu->aad.ptr + 1, bytes);
+  if (e != AAD_APIRESULT_OK) return e;
+  CU(cudaMemcpyAsync(reconstructed, gpu->wav.ptr, (size_t)geo.channels * num_samples * 2, cudaMemcpyDeviceToHost, gpu->s_run),
+     "D2H wav");
+  CU(cudaStreamSynchronize(gpu->s_run), "sync");
+  if (encoded_size) *encoded_size = (uint32_t)bytes;
   return AAD_APIRESULT_OK;
 }

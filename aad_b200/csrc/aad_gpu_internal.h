@@ -23,7 +23,7 @@ struct AADGpu {
   int device;
   cudaStream_t s_in, s_run, s_out;
   cudaEvent_t ev_in[16], ev_run[16];
-  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut;
+  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav;
   int lut_ready;
 };
 
@@ -39,6 +39,9 @@ int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes);
 struct AADGpu *aadgpu_default(void);
 
 uint32_t aadgpu_max_channels(void);
+
+/* AADDecoder_DecodeHeader's result must also pass this before a kernel sees it (aad_decoder.c) */
+AADApiResult aaddec_check_header(const struct AADHeaderInfo *h);
 
 /* Single-stream paths behind AADEncoder_EncodeWhole / AADDecoder_DecodeWhole / _DecodeBlock.
  * Host pointers, int32 PCM (the reference API type). */

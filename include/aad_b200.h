@@ -84,6 +84,22 @@ AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
 AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                 const uint8_t *aad, const uint32_t *sizes, int16_t *pcm);
 
+/* ---- one stream in WAV order (interleaved int16), host pointers: what `aad -e / -d / -r` call ---- */
+/* src/main.c:141-227 (execute_encode) without the host-side int32 shuffle: the 16-bit samples of a
+ * WAV data chunk are copied as they are and de-interleaved on the device. */
+AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *param,
+                                        const int16_t *interleaved, uint32_t num_samples,
+                                        uint8_t *data, uint32_t data_size, uint32_t *output_size);
+/* src/main.c:61-138 (execute_decode): the stream's own header says how many channels / samples come
+ * out; capacity_samples (per channel) must cover it. */
+AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
+                                        int16_t *interleaved, uint32_t capacity_samples);
+/* src/main.c:275-346 (execute_reconstruction_core): encode then decode, the stream stays in HBM.
+ * encoded_size (nullable) receives the size the .aad file would have had. */
+AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *param,
+                                             const int16_t *interleaved, uint32_t num_samples,
+                                             int16_t *reconstructed, uint32_t *encoded_size);
+
 /* ---- deterministic synthetic PCM (bench / tests), SURVEY.md 8(d) ------------------------ */
 AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                      uint32_t first_stream, int16_t *pcm_dev, void *stream);
