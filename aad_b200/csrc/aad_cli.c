@@ -9,7 +9,7 @@
  *   - the samples of a 16-bit WAV go to the GPU as they lie in the file; de-interleaving, the codec
  *     and re-interleaving run on the device (AADGpu_*Interleaved16);
  *   - -r / -g / -c keep the encoded stream in HBM between encode and decode.
- * Additions: --device N, and --batch LIST for -e / -d (one "INPUT OUTPUT" pair per line; files of
+ * Additions: --device N | a,b,c | all, and --batch LIST for -e / -d (one "INPUT OUTPUT" pair per line; files of
  * the same shape are encoded / decoded by ONE kernel launch through the batch API).
  */
 #define _POSIX_C_SOURCE 200809L
@@ -52,7 +52,7 @@ static const struct option_spec k_specs[] = {
   { 's', "max-block-size", 1, "Specify max block size (default: 1024)" },
   { 't', "num-encode-trials", 1, "Specify number of encode Trials (default: 2)" },
   { 'm', "ms-conversion", 0, "Switch to use LR to MS conversion (default: no)" },
-  { 'D', "device", 1, "CUDA device index (default: 0)" },
+  { 'D', "device", 1, "CUDA device(s): index, comma separated list, or \"all\" (default: 0); with several, -d shards one file by block range and --batch shards files" },
   { 'B', "batch", 1, "With -e / -d: file listing one \"INPUT OUTPUT\" pair per line, processed as batches" },
   { 'h', "help", 0, "Show help message" },
   { 'v', "version", 0, "Show version information" },
@@ -322,6 +322,8 @@ static int execute_encode(struct AADGpu *gpu, const char *in_name, const char *o
   return rc;
 }
 
+static struct AADGpuGroup *g_group = NULL;   /* set when --device names more than one GPU */
+
 static int execute_decode(struct AADGpu *gpu, const char *in_name, const char *out_name)
 {
   size_t size = 0;
@@ -343,7 +345,9 @@ static int execute_decode(struct AADGpu *gpu, const char *in_name, const char *o
   int rc = 1;
   if (image != NULL) {
     aadwav_write_header(image, h.num_channels, h.sampling_rate, 16, h.num_samples);
-    r = AADGpu_DecodeInterleaved16(gpu, data, (uint32_t)size, (int16_t *)(void *)(image + AADWAV_HEADER_BYTES), h.num_samples);
+    int16_t *samples = (int16_t *)(void *)(image + AADWAV_HEADER_BYTES);
+    r = g_group ? AADGpuGroup_DecodeInterleaved16(g_group, data, (uint32_t)size, samples, h.num_samples)   /* by block range */
+                : AADGpu_DecodeInterleaved16(gpu, data, (uint32_t)size, samples, h.num_samples);
     if (r != AAD_APIRESULT_OK) fprintf(stderr, "Failed to decode. API result: %d %s\n", r, AADGpu_LastError());
     else rc = write_file(out_name, image, AADWAV_HEADER_BYTES + count * 2);
     io_free(image);
@@ -498,7 +502,7 @@ static int execute_encode_batch(struct AADGpu *gpu, const char *manifest, const 
           for (uint32_t s = 0; s < ii->num_samples; s++) dst[c * b.pcm_channel_stride + s] = items[i].wav.pcm16[(size_t)s * C + c];
         lens[m++] = ii->num_samples;
       }
-      r = AADGpu_EncodeBatch(gpu, &b, pcm, lens, aad, sizes);
+      r = g_group ? AADGpuGroup_EncodeBatch(g_group, &b, pcm, lens, aad, sizes) : AADGpu_EncodeBatch(gpu, &b, pcm, lens, aad, sizes);
       if (r != AAD_APIRESULT_OK) fprintf(stderr, "Failed to encode. API result:%d %s\n", r, AADGpu_LastError());
     }
     size_t m = 0;
@@ -582,7 +586,7 @@ static int execute_decode_batch(struct AADGpu *gpu, const char *manifest)
         memcpy(aad + m * b.aad_stream_stride, items[i].aad, items[i].aad_size);
         sizes[m++] = (uint32_t)items[i].aad_size;
       }
-      r = AADGpu_DecodeBatch(gpu, &b, aad, sizes, pcm);
+      r = g_group ? AADGpuGroup_DecodeBatch(g_group, &b, aad, sizes, pcm) : AADGpu_DecodeBatch(gpu, &b, aad, sizes, pcm);
     }
     if (r != AAD_APIRESULT_OK) fprintf(stderr, "Failed to decode. API result: %d %s\n", r, AADGpu_LastError());
     size_t m = 0;
@@ -673,8 +677,36 @@ int main(int argc, char **argv)
     return 1;
   }
 
-  /* the stock reference handles 1 or 2 channels; keep its limit unless asked otherwise */
-  struct AADGpu *gpu = AADGpu_Create(o.device ? atoi(o.device) : 0);
+  /* --device: one index, a list, or "all" */
+  int devices[16], num_devices = 0;
+  const char *spec = o.device ? o.device : "0";
+  if (strcmp(spec, "all") == 0) {
+    num_devices = AADGpu_DeviceCount();
+    if (num_devices > 16) num_devices = 16;
+    for (int d = 0; d < num_devices; d++) devices[d] = d;
+  } else {
+    const char *p = spec;
+    while (*p != '\0' && num_devices < 16) {
+      char *end = NULL;
+      const long v = strtol(p, &end, 10);
+      if (end == p || v < 0) { num_devices = 0; break; }
+      devices[num_devices++] = (int)v;
+      p = (*end == ',') ? end + 1 : end;
+      if (*end != ',' && *end != '\0') { num_devices = 0; break; }
+    }
+  }
+  if (num_devices == 0) {
+    fprintf(stderr, "%s: no usable CUDA device in \"%s\" (%d visible; this program has no CPU fallback) \n", argv[0], spec,
+            AADGpu_DeviceCount());
+    return 1;
+  }
+  struct AADGpu *gpu = NULL;
+  if (num_devices > 1) {
+    g_group = AADGpuGroup_Create(devices, num_devices);
+    gpu = AADGpuGroup_Device(g_group, 0);
+  } else {
+    gpu = AADGpu_Create(devices[0]);
+  }
   if (gpu == NULL) {
     fprintf(stderr, "%s: %s \n", argv[0], AADGpu_LastError());
     return 1;
@@ -685,6 +717,7 @@ int main(int argc, char **argv)
   else if (mode == MODE_ENCODE) rc = execute_encode(gpu, o.files[0], o.files[1], &cli);
   else if (mode == MODE_DECODE) rc = execute_decode(gpu, o.files[0], o.files[1]);
   else rc = execute_analysis(gpu, mode, o.files[0], o.files[1], &cli);
-  AADGpu_Destroy(gpu);
+  if (g_group) AADGpuGroup_Destroy(g_group);
+  else AADGpu_Destroy(gpu);
   return rc;
 }

@@ -763,3 +763,251 @@ AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AA
   if (encoded_size) *encoded_size = (uint32_t)bytes;
   return AAD_APIRESULT_OK;
 }
+
+/* ---- several devices of one box: shard, run one host thread per device, done ---------------- */
+/*
+ * The codec has no exchange step: batches shard by stream, one long stream
+ * shards its DECODE by block range (every block header reloads the chain state,
+ * src/aad_decoder.c:364-380).  Each device writes its own disjoint slice of the caller's
+ * buffers, so reassembly is the layout itself; no NCCL, no peer copies.  One stream cannot be
+ * ENCODED in shards bit-exactly (src/aad_encoder.c:853-886 carries state), so there is no such call.
+ */
+struct AADGpuGroup {
+  int size;
+  struct AADGpu *gpu[AADGPU_MAX_GROUP];
+};
+
+struct AADGpuGroup *AADGpuGroup_Create(const int *devices, int num_devices)
+{
+  const int visible = AADGpu_DeviceCount();
+  if (devices == NULL) num_devices = (num_devices <= 0 || num_devices > visible) ? visible : num_devices;
+  if (num_devices <= 0 || num_devices > AADGPU_MAX_GROUP) {
+    aadgpu_set_error("AADGpuGroup_Create: no usable CUDA devices (this library has no CPU fallback)");
+    return NULL;
+  }
+  struct AADGpuGroup *g = (struct AADGpuGroup *)calloc(1, sizeof(*g));
+  if (!g) return NULL;
+  for (int i = 0; i < num_devices; i++) {
+    g->gpu[i] = AADGpu_Create(devices ? devices[i] : i);
+    if (g->gpu[i] == NULL) {
+      AADGpuGroup_Destroy(g);
+      return NULL;
+    }
+    g->size++;
+  }
+  return g;
+}
+
+void AADGpuGroup_Destroy(struct AADGpuGroup *g)
+{
+  if (!g) return;
+  for (int i = 0; i < g->size; i++) AADGpu_Destroy(g->gpu[i]);
+  free(g);
+}
+
+int AADGpuGroup_Size(const struct AADGpuGroup *g) { return g ? g->size : 0; }
+struct AADGpu *AADGpuGroup_Device(const struct AADGpuGroup *g, int index) { return (g && index >= 0 && index < g->size) ? g->gpu[index] : NULL; }
+
+/* contiguous, balanced: the first (n % parts) shards get one more (aad_b200/shard.py: split_range) */
+static void split_range(uint64_t n, int parts, int index, uint64_t *begin, uint64_t *end)
+{
+  const uint64_t base = n / (uint64_t)parts, extra = n % (uint64_t)parts;
+  const uint64_t i = (uint64_t)index;
+  *begin = i * base + (i < extra ? i : extra);
+  *end = *begin + base + (i < extra ? 1u : 0u);
+}
+
+enum group_op { GROUP_ENCODE_BATCH, GROUP_DECODE_BATCH, GROUP_DECODE_STREAM };
+
+struct group_task {
+  enum group_op op;
+  struct AADGpu *gpu;
+  struct AADGpuBatch batch;
+  const int16_t *pcm_in;
+  int16_t *pcm_out;
+  const uint32_t *lens;
+  const uint8_t *aad_in;
+  uint8_t *aad_out;
+  uint32_t *sizes_out;
+  /* GROUP_DECODE_STREAM */
+  struct AADHeaderInfo header;
+  uint32_t data_size, block_begin, block_end;
+  AADApiResult result;
+  char error[320];
+};
+
+static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
+                                        uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved);
+
+static void *group_worker(void *arg)
+{
+  struct group_task *t = (struct group_task *)arg;
+  switch (t->op) {
+    case GROUP_ENCODE_BATCH:
+      t->result = AADGpu_EncodeBatch(t->gpu, &t->batch, t->pcm_in, t->lens, t->aad_out, t->sizes_out);
+      break;
+    case GROUP_DECODE_BATCH:
+      t->result = AADGpu_DecodeBatch(t->gpu, &t->batch, t->aad_in, t->lens, t->pcm_out);
+      break;
+    default:
+      t->result = decode_stream_range(t->gpu, &t->header, t->aad_in, t->data_size, t->block_begin, t->block_end, t->pcm_out);
+      break;
+  }
+  snprintf(t->error, sizeof(t->error), "%s", AADGpu_LastError());   /* thread-local: carry it to the caller */
+  return NULL;
+}
+
+static AADApiResult group_run(struct group_task *tasks, int n)
+{
+  pthread_t th[AADGPU_MAX_GROUP];
+  int started[AADGPU_MAX_GROUP];
+  for (int i = 0; i < n; i++) {
+    started[i] = pthread_create(&th[i], NULL, group_worker, &tasks[i]) == 0;
+    if (!started[i]) group_worker(&tasks[i]);    /* no thread: do it here, still correct */
+  }
+  AADApiResult r = AAD_APIRESULT_OK;
+  for (int i = 0; i < n; i++) {
+    if (started[i]) pthread_join(th[i], NULL);
+    if (tasks[i].result != AAD_APIRESULT_OK && r == AAD_APIRESULT_OK) {
+      r = tasks[i].result;
+      aadgpu_set_error(tasks[i].error);
+    }
+  }
+  return r;
+}
+
+AADApiResult AADGpuGroup_EncodeBatch(struct AADGpuGroup *g, const struct AADGpuBatch *batch, const int16_t *pcm,
+                                     const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes)
+{
+  if (!g || !batch || !pcm || !aad) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct group_task tasks[AADGPU_MAX_GROUP];
+  int n = 0;
+  for (int d = 0; d < g->size; d++) {
+    uint64_t i0, i1;
+    split_range(batch->num_streams, g->size, d, &i0, &i1);
+    if (i1 == i0) continue;
+    struct group_task *t = &tasks[n++];
+    memset(t, 0, sizeof(*t));
+    t->op = GROUP_ENCODE_BATCH;
+    t->gpu = g->gpu[d];
+    t->batch = *batch;
+    t->batch.num_streams = (uint32_t)(i1 - i0);
+    t->pcm_in = pcm + i0 * batch->pcm_stream_stride;
+    t->lens = num_samples ? num_samples + i0 : NULL;
+    t->aad_out = aad + i0 * batch->aad_stream_stride;
+    t->sizes_out = out_sizes ? out_sizes + i0 : NULL;
+  }
+  /* an empty batch still gets the argument checks of the single-device call */
+  if (n == 0) return AADGpu_EncodeBatch(g->gpu[0], batch, pcm, num_samples, aad, out_sizes);
+  return group_run(tasks, n);
+}
+
+AADApiResult AADGpuGroup_DecodeBatch(struct AADGpuGroup *g, const struct AADGpuBatch *batch, const uint8_t *aad,
+                                     const uint32_t *sizes, int16_t *pcm)
+{
+  if (!g || !batch || !pcm || !aad) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct group_task tasks[AADGPU_MAX_GROUP];
+  int n = 0;
+  for (int d = 0; d < g->size; d++) {
+    uint64_t i0, i1;
+    split_range(batch->num_streams, g->size, d, &i0, &i1);
+    if (i1 == i0) continue;
+    struct group_task *t = &tasks[n++];
+    memset(t, 0, sizeof(*t));
+    t->op = GROUP_DECODE_BATCH;
+    t->gpu = g->gpu[d];
+    t->batch = *batch;
+    t->batch.num_streams = (uint32_t)(i1 - i0);
+    t->aad_in = aad + i0 * batch->aad_stream_stride;
+    t->lens = sizes ? sizes + i0 : NULL;
+    t->pcm_out = pcm + i0 * batch->pcm_stream_stride;
+  }
+  if (n == 0) return AADGpu_DecodeBatch(g->gpu[0], batch, aad, sizes, pcm);
+  return group_run(tasks, n);
+}
+
+/* blocks [b0, b1) of one stream -> interleaved samples [b0*spb, min(b1*spb, ns)) of the caller's buffer */
+static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
+                                        uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved)
+{
+  const uint32_t C = h->num_channels, spb = h->num_samples_per_block, bs = h->block_size, ns = h->num_samples;
+  const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < ns) ? (uint64_t)b1 * spb : ns;
+  if (b1 <= b0 || s1 <= s0) return AAD_APIRESULT_OK;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  const uint64_t count = s1 - s0;
+  const uint64_t pitch = round_up64(count, 64);
+  const uint64_t byte0 = AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
+  uint64_t byte1 = AADF_FILE_HEADER_BYTES + (uint64_t)b1 * bs;
+  if (byte1 > data_size) byte1 = data_size;
+  const uint64_t span = byte1 > byte0 ? byte1 - byte0 : 0;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 256)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * count * 2)) return AAD_APIRESULT_NG;
+  cudaStream_t s = gpu->s_run;
+  uint8_t *d_shard = (uint8_t *)gpu->aad.ptr;       /* block b0 at the (256-byte aligned) start */
+  if (span) CU(cudaMemcpyAsync(d_shard, data + byte0, (size_t)span, cudaMemcpyHostToDevice, s), "H2D aad shard");
+  CU(cudaMemsetAsync(gpu->pcm.ptr, 0, (size_t)C * pitch * 2, s), "memset pcm");
+  struct aadk_decode_params p;
+  memset(&p, 0, sizeof(p));
+  /* the kernels address block b at aad + 31 + b*block_size and sample b*spb of a row at pcm + b*spb:
+   * shift both bases back so the shard's first block and sample land at the buffers' starts (the
+   * shifted pointers are only ever dereferenced inside the shard) */
+  p.aad = d_shard - byte0;
+  p.aad_stride = 0;
+  p.uniform_size = (uint32_t)byte1;
+  p.num_streams = 1;
+  p.geo.channels = C;
+  p.geo.bits = h->bits_per_sample;
+  p.geo.block_size = bs;
+  p.geo.samples_per_block = spb;
+  p.geo.ms = (h->ch_process_method == AAD_CH_PROCESS_METHOD_MS) ? 1u : 0u;
+  p.block_begin = b0;
+  p.block_end = b1;
+  p.uniform_samples = ns;
+  p.pcm = (int16_t *)gpu->pcm.ptr - s0;
+  p.pcm_clip_stride = 0;
+  p.pcm_ch_stride = pitch;
+  CU((cudaError_t)aadk_launch_decode(&p, s), "decode kernel launch");
+  CU((cudaError_t)aadk_launch_interleave16((const int16_t *)gpu->pcm.ptr, pitch, (int16_t *)gpu->wav.ptr, C, (uint32_t)count, s),
+     "interleave kernel launch");
+  CU(cudaMemcpyAsync(interleaved + s0 * C, gpu->wav.ptr, (size_t)C * count * 2, cudaMemcpyDeviceToHost, s), "D2H wav shard");
+  CU(cudaStreamSynchronize(s), "sync");
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_t *data, uint32_t data_size,
+                                             int16_t *interleaved, uint32_t capacity_samples)
+{
+  if (!g || !data || !interleaved) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct AADHeaderInfo h;
+  const AADApiResult r = parse_stream_header(data, data_size, &h);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (capacity_samples < h.num_samples) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  /* blocks the data reaches (src/aad_decoder.c:514-534); samples of later blocks are zero */
+  const uint32_t by_samples = aadf_num_blocks(h.num_samples, h.num_samples_per_block);
+  const uint64_t payload = (uint64_t)data_size - AADF_FILE_HEADER_BYTES;
+  const uint64_t by_bytes = (payload + h.block_size - 1) / h.block_size;
+  const uint32_t blocks = (uint32_t)(by_bytes < by_samples ? by_bytes : by_samples);
+  const uint64_t decoded = ((uint64_t)blocks * h.num_samples_per_block < h.num_samples)
+                               ? (uint64_t)blocks * h.num_samples_per_block : h.num_samples;
+  if (decoded < h.num_samples)
+    memset(interleaved + decoded * h.num_channels, 0, (size_t)(h.num_samples - decoded) * h.num_channels * 2);
+  struct group_task tasks[AADGPU_MAX_GROUP];
+  int n = 0;
+  for (int d = 0; d < g->size; d++) {
+    uint64_t b0, b1;
+    split_range(blocks, g->size, d, &b0, &b1);
+    if (b1 == b0) continue;
+    struct group_task *t = &tasks[n++];
+    memset(t, 0, sizeof(*t));
+    t->op = GROUP_DECODE_STREAM;
+    t->gpu = g->gpu[d];
+    t->header = h;
+    t->aad_in = data;
+    t->data_size = data_size;
+    t->block_begin = (uint32_t)b0;
+    t->block_end = (uint32_t)b1;
+    t->pcm_out = interleaved;
+  }
+  return n ? group_run(tasks, n) : AAD_APIRESULT_OK;
+}

@@ -13,6 +13,7 @@
 #include "aad_kernels.h"
 
 #define AADGPU_PIPE_STREAMS 3   /* H2D, kernels, D2H */
+#define AADGPU_MAX_GROUP 16     /* devices in one AADGpuGroup */
 
 struct aadgpu_buffer {
   void *ptr;

@@ -35,6 +35,8 @@ class GpuApi:
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
         "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath",
         "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16",
+        "AADGpuGroup_Create", "AADGpuGroup_Destroy", "AADGpuGroup_Size", "AADGpuGroup_Device",
+        "AADGpuGroup_EncodeBatch", "AADGpuGroup_DecodeBatch", "AADGpuGroup_DecodeInterleaved16",
     )
 
     def __init__(self, lib):
@@ -65,6 +67,13 @@ class GpuApi:
             "AADGpu_EncodeInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, u32, C.POINTER(u32)]),
             "AADGpu_DecodeInterleaved16": (C.c_int, [vp, vp, u32, vp, u32]),
             "AADGpu_ReconstructInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, C.POINTER(u32)]),
+            "AADGpuGroup_Create": (vp, [C.POINTER(C.c_int), C.c_int]),
+            "AADGpuGroup_Destroy": (None, [vp]),
+            "AADGpuGroup_Size": (C.c_int, [vp]),
+            "AADGpuGroup_Device": (vp, [vp, C.c_int]),
+            "AADGpuGroup_EncodeBatch": (C.c_int, [vp, bp, vp, vp, vp, vp]),
+            "AADGpuGroup_DecodeBatch": (C.c_int, [vp, bp, vp, vp, vp]),
+            "AADGpuGroup_DecodeInterleaved16": (C.c_int, [vp, vp, u32, vp, u32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)

@@ -100,6 +100,27 @@ AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AA
                                              const int16_t *interleaved, uint32_t num_samples,
                                              int16_t *reconstructed, uint32_t *encoded_size);
 
+/* ---- several GPUs of one box ------------------------------------------------------------------- */
+/* One context and one host thread per device.  Batches shard by stream; one long stream shards its
+ * DECODE by block range (every block header reloads the chain state, src/aad_decoder.c:364-380).
+ * Every device writes its own disjoint slice of the caller's buffers: no collective, no peer copy.
+ * There is no sharded encode of ONE stream: the reference carries state from block to block
+ * (src/aad_encoder.c:853-886), so its bytes cannot be produced in independent pieces. */
+struct AADGpuGroup;
+/* devices == NULL: the first num_devices visible devices (all of them when num_devices <= 0) */
+struct AADGpuGroup *AADGpuGroup_Create(const int *devices, int num_devices);
+void AADGpuGroup_Destroy(struct AADGpuGroup *group);
+int AADGpuGroup_Size(const struct AADGpuGroup *group);
+struct AADGpu *AADGpuGroup_Device(const struct AADGpuGroup *group, int index);
+/* same arguments and results as AADGpu_EncodeBatch / AADGpu_DecodeBatch / AADGpu_DecodeInterleaved16 */
+AADApiResult AADGpuGroup_EncodeBatch(struct AADGpuGroup *group, const struct AADGpuBatch *batch,
+                                     const int16_t *pcm, const uint32_t *num_samples,
+                                     uint8_t *aad, uint32_t *out_sizes);
+AADApiResult AADGpuGroup_DecodeBatch(struct AADGpuGroup *group, const struct AADGpuBatch *batch,
+                                     const uint8_t *aad, const uint32_t *sizes, int16_t *pcm);
+AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *group, const uint8_t *data, uint32_t data_size,
+                                             int16_t *interleaved, uint32_t capacity_samples);
+
 /* ---- deterministic synthetic PCM (bench / tests), SURVEY.md 8(d) ------------------------ */
 AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                      uint32_t first_stream, int16_t *pcm_dev, void *stream);
