@@ -36,8 +36,9 @@ METRIC = "encode+decode round-trip throughput (bit-exact AAD ADPCM)"
 UNIT = "Msamples/s"
 RATE, CLIP_SAMPLES, CHANNELS, BITS, MAX_BLOCK, TRIALS = 44100, 441000, 1, 4, 1024, 2
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel
-# at the default workload; filled in from profiles/ (None until a capture exists)
-NCU_TRAFFIC_BYTES = None
+# (aad_encode_fast<4,0>) at the default workload: profiles/r01_v5_encode.md.  Reported only for
+# that exact workload.
+NCU_TRAFFIC_BYTES = 35.5e9
 
 
 def parse_args():
@@ -333,6 +334,7 @@ def run_b200_arm(args):
 
     if rank == 0:
         peak, peak_src = hbm_peak()
+        default_workload = (N, n, ch, args.bits, args.trials) == (12500, CLIP_SAMPLES, CHANNELS, BITS, TRIALS)
         enc_gbs = samples_per_step * bytes_per_sample / (enc_ms * 1e-3) / 1e9
         dec_gbs = samples_per_step * bytes_per_sample / (dec_ms * 1e-3) / 1e9
         dominant, dom_gbs = ("aad_encode", enc_gbs) if enc_ms >= dec_ms else ("aad_decode", dec_gbs)
@@ -344,9 +346,11 @@ def run_b200_arm(args):
             "decode_msamples_s": round(samples_per_step * world / (dec_ms * 1e-3) / 1e6, 3),
             "kernel_ms": {"encode": round(enc_ms, 3), "decode": round(dec_ms, 3)},
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(dom_gbs, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(dom_gbs / peak, 5), "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                         "frac": round(dom_gbs / peak, 5),
+                         "traffic": NCU_TRAFFIC_BYTES if default_workload and dominant == "aad_encode" else None,
+                         "algorithmic_bytes_per_launch": round(samples_per_step * bytes_per_sample), "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": round(bytes_per_sample, 4),
-                         "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5"},
+                         "note": "12,500 serial chains per GPU: latency/issue bound, not HBM bound (DESIGN.md 4.2, profiles/r01_v5_encode.md)"},
             "roofline_decode": {"bound": "hbm", "kernel": "aad_decode", "achieved": round(dec_gbs, 2), "peak": peak,
                                 "unit": "GB/s", "frac": round(dec_gbs / peak, 5)},
             "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
