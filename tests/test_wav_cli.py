@@ -303,6 +303,27 @@ def test_cli_differential_against_the_reference_cli(tmp_path):
 
 
 @pytest.mark.gpu
+def test_the_unmodified_reference_main_runs_on_the_b200_library(tmp_path):
+    """INTEGRATION.md section 1, executed: src/main.c + wav.c + command_line_parser.c compiled untouched
+    and linked against libaad_b200.so instead of the reference codec (oracle/Makefile:
+    _ref/aad_ref_cli_b200) reproduce the reference's own output files."""
+    drop_in = aadtest.ROOT / "oracle" / "_ref" / "aad_ref_cli_b200"
+    if not drop_in.exists():
+        pytest.skip("oracle/_ref/aad_ref_cli_b200 did not travel")
+    run = lambda *a: subprocess.run([str(drop_in), *map(str, a)], capture_output=True, text=True, timeout=300)
+    for stem in ("sin300Hz", "sin300Hz_mono"):
+        r = run("-e", aadtest.GOLDEN / f"{stem}.wav", tmp_path / "o.aad")
+        assert r.returncode == 0, r.stderr
+        assert (tmp_path / "o.aad").read_bytes() == (aadtest.GOLDEN / f"{stem}.aad").read_bytes()
+        r = run("-d", aadtest.GOLDEN / f"{stem}.aad", tmp_path / "o.wav")
+        assert r.returncode == 0, r.stderr
+        assert (tmp_path / "o.wav").read_bytes() == (aadtest.GOLDEN / f"{stem}_decoded.wav").read_bytes()
+    r = run("-c", "-b", "3", aadtest.GOLDEN / "bunny1.wav")
+    want = subprocess.run([str(REF_CLI), "-c", "-b", "3", str(aadtest.GOLDEN / "bunny1.wav")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == want.stdout
+
+
+@pytest.mark.gpu
 def test_cli_batch_mode_equals_file_by_file(tmp_path, oracle):
     """--batch: files of one shape share a launch; every output equals the single-file result."""
     rng = np.random.default_rng(5)
