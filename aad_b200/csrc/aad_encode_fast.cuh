@@ -393,6 +393,31 @@ __device__ __forceinline__ void enc_job_put_unit(EncJob<MS> &j, const uint32_t h
   }
 }
 
+/* the full 16-sample units [u0, units) of one job.  KIND 0: dry run (error sum only), 1: emitting
+ * (codes only): two copies of the loop, 3 instructions per sample shorter each than one that does both */
+template <int BITS, int MS, int KIND>
+__device__ __forceinline__ void enc_job_units(EncJob<MS> &j, const EncSource<MS> &src, uint32_t u0, bool mono,
+                                              uint32_t gstride, const EncShared &sh)
+{
+  EncChain &c = j.c;
+  for (uint32_t u = u0; u < j.units; u++) {
+    EncRing<MS>::template wait<kEncAhead - 1>();
+    EncUnit<MS> cur;
+    cur.read(j.ring, u & (kEncSlots - 1), src);
+    enc_job_request<MS>(j, src, u + kEncAhead);
+    EncRing<MS>::commit();
+    uint32_t half[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < kEncUnit; k++) {
+      int32_t q;
+      const uint32_t code = enc_sample<BITS>(c, cur.get(src, k), sh, q);
+      if (KIND != 0) half[k >> 3] = (half[k >> 3] << BITS) + code;
+      if (KIND != 1) enc_add_square(j.sum, q);
+    }
+    if (KIND == 1) enc_job_put_unit<BITS, MS>(j, half, mono, gstride);
+  }
+}
+
 /* units [u0, units) of one job, then its last samples one by one; the emitting pass rounds up
  * to whole groups with zero samples (src/aad_encoder.c:592-593).  Units u0 .. u0+kEncAhead-1
  * have been requested already. */
@@ -406,21 +431,8 @@ __device__ __forceinline__ void enc_job_finish(EncJob<MS> &j, const EncSource<MS
   const bool mono = (C == 1);                      /* uniform: contiguous code bytes -> word stores */
   const uint32_t gstride = C * GB;
   EncChain &c = j.c;
-  for (uint32_t u = u0; u < j.units; u++) {
-    EncRing<MS>::template wait<kEncAhead - 1>();
-    EncUnit<MS> cur;
-    cur.read(j.ring, u & (kEncSlots - 1), src);
-    enc_job_request<MS>(j, src, u + kEncAhead);
-    EncRing<MS>::commit();
-    uint32_t half[2] = {0u, 0u};
-#pragma unroll
-    for (int k = 0; k < kEncUnit; k++) {
-      int32_t q;
-      half[k >> 3] = (half[k >> 3] << BITS) + enc_sample<BITS>(c, cur.get(src, k), sh, q);
-      enc_add_square(j.sum, q);
-    }
-    if (j.emit) enc_job_put_unit<BITS, MS>(j, half, mono, gstride);
-  }
+  if (j.emit) enc_job_units<BITS, MS, 1>(j, src, u0, mono, gstride, sh);
+  else enc_job_units<BITS, MS, 0>(j, src, u0, mono, gstride, sh);
   const uint32_t total = (j.n > AADF_TAPS) ? j.n - AADF_TAPS : 0u;
   const uint32_t limit = j.first + j.n;
   const uint32_t rest = total - j.units * kEncUnit;
@@ -461,13 +473,55 @@ __device__ __forceinline__ void enc_run_job(EncJob<MS> &j, const EncSource<MS> &
   enc_job_finish<BITS, MS>(j, src, 0u, C, sh);
 }
 
+/* Two DRY passes of the same thread at once (the baseline pass and the first trial pass of a block
+ * both start from the carried state, so they are independent).  While both have full units left
+ * their sample recurrences are interleaved instruction by instruction: one fills the other's
+ * dependency stalls (a lone chain issues on ~45 % of its cycles), ~130 cycles per sample pair
+ * instead of 2 x 95.  x keeps its error sum; y only its state.  What is left of either is finished
+ * alone. */
+template <int BITS, int MS>
+__device__ __forceinline__ void enc_run_pair(EncJob<MS> &x, EncJob<MS> &y, const EncSource<MS> &src, uint32_t ch,
+                                             uint32_t C, const EncShared &sh)
+{
+  enc_job_begin<BITS, MS>(x, src, ch, C);
+  enc_job_begin<BITS, MS>(y, src, ch, C);
+#pragma unroll
+  for (int d = 0; d < kEncAhead; d++) {
+    enc_job_request<MS>(x, src, d);
+    enc_job_request<MS>(y, src, d);
+    EncRing<MS>::commit();
+  }
+  const uint32_t common = (x.run && y.run) ? min(x.units, y.units) : 0u;
+  for (uint32_t u = 0; u < common; u++) {
+    EncRing<MS>::template wait<kEncAhead - 1>();
+    EncUnit<MS> ux, uy;
+    ux.read(x.ring, u & (kEncSlots - 1), src);
+    uy.read(y.ring, u & (kEncSlots - 1), src);
+    enc_job_request<MS>(x, src, u + kEncAhead);
+    enc_job_request<MS>(y, src, u + kEncAhead);
+    EncRing<MS>::commit();
+#pragma unroll
+    for (int k = 0; k < kEncUnit; k++) {
+      int32_t qx, qy;
+      (void)enc_sample<BITS>(x.c, ux.get(src, k), sh, qx);
+      (void)enc_sample<BITS>(y.c, uy.get(src, k), sh, qy);
+      enc_add_square(x.sum, qx);
+    }
+  }
+#pragma unroll 1
+  for (int which = 0; which < 2; which++) enc_job_finish<BITS, MS>(which ? y : x, src, common, C, sh);
+}
+
 /* src/aad_encoder.c:465: sqrt(sum / n) in double; 0 for n < 4 (src/aad_encoder.c:444-447) */
 __device__ __forceinline__ double enc_rmse(double sum, uint32_t n)
 {
   return (n < AADF_TAPS) ? 0.0 : sqrt(sum / (double)n);
 }
 
-template <int BITS, int MS>
+/* PAIR: run the two independent dry passes of a block interleaved in one thread (enc_run_pair).
+ * Pays when chains are scarce and every warp has a scheduler to itself; costs registers (a second
+ * chain and sample unit), so launches with many chains use PAIR = 0. */
+template <int BITS, int MS, int PAIR>
 __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params p)
 {
   extern __shared__ __align__(16) unsigned char enc_smem[];
@@ -510,9 +564,10 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   const uint32_t trials = p.trials;
   const uint32_t nblk = min(aadf_num_blocks(ns, spb), p.block_end);
 
-  EncJob<MS> job;
+  EncJob<MS> job, job2;
   job.ring.base = (uint32_t)__cvta_generic_to_shared(enc_smem) + kEncLutBytes +
-                  (threadIdx.x >> 5) * EncRing<MS>::kWarpBytes + (threadIdx.x & 31u) * 16u;
+                  (threadIdx.x >> 5) * ((PAIR ? 2u : 1u) * EncRing<MS>::kWarpBytes) + (threadIdx.x & 31u) * 16u;
+  job2.ring.base = job.ring.base + EncRing<MS>::kWarpBytes;
 
   for (uint32_t b = p.block_begin; b < nblk; b++) {
     const uint32_t first = b * spb;
@@ -526,7 +581,17 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
     EncState run = S, best = S, cand = S;
     double best_rmse = 0.0;
     const uint32_t dry = trials ? 1u + 2u * trials : 0u;
-    for (uint32_t k = 0; k <= dry; k++) {
+    uint32_t k = 0;
+    if (PAIR && dry && b > 0) {   /* passes 0 and 1 both start from the carried state: run them together */
+      job.c.set(S);  job.first = first;        job.n = n;    job.run = true;  job.emit = false;
+      job2.c.set(S); job2.first = first - spb; job2.n = spb; job2.run = true; job2.emit = false;
+      job.blk = job2.blk = out;
+      enc_run_pair<BITS, MS>(job, job2, src, ch, C, sh);
+      best_rmse = enc_rmse(job.sum, n);
+      if (job2.run) run = job2.c.state();
+      k = 2;
+    }
+    for (; k <= dry; k++) {
       const bool emit = (k == dry);
       const bool on_prev = !emit && (k & 1u) != 0u;
       if (on_prev && b == 0) continue;
@@ -572,13 +637,13 @@ inline bool enc_fast_eligible(const aadk_encode_params &p)
   return true;
 }
 
-template <int BITS, int MS>
+template <int BITS, int MS, int PAIR>
 int enc_fast_launch_as(const aadk_encode_params &p, cudaStream_t s)
 {
   const uint64_t lanes = (uint64_t)p.num_streams * p.geo.channels;
-  const size_t ring_bytes = EncRing<MS>::kWarpBytes;
+  const size_t ring_bytes = (size_t)(PAIR ? 2 : 1) * EncRing<MS>::kWarpBytes;
   /* per device, so set on every launch (cheap) */
-  cudaError_t e = cudaFuncSetAttribute(aad_encode_fast<BITS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(aad_encode_fast<BITS, MS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kEncLutBytes + 8 * ring_bytes));
   if (e != cudaSuccess) return (int)e;
   /* The step table is per CTA.  Smallest CTA that keeps every chain resident in one wave, so few
@@ -591,7 +656,7 @@ int enc_fast_launch_as(const aadk_encode_params &p, cudaStream_t s)
   uint64_t best_resident = 0;
   for (unsigned cand = 32; cand <= 256 && block == 0; cand *= 2) {
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aad_encode_fast<BITS, MS>, (int)cand,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aad_encode_fast<BITS, MS, PAIR>, (int)cand,
                                                       kEncLutBytes + (cand / 32) * ring_bytes);
     if (e != cudaSuccess) return (int)e;
     const uint64_t resident = (uint64_t)per_sm * sms * cand;
@@ -601,15 +666,19 @@ int enc_fast_launch_as(const aadk_encode_params &p, cudaStream_t s)
   if (block == 0) block = best_block;
   const unsigned grid = (unsigned)((lanes + block - 1) / block);
   const size_t smem = kEncLutBytes + (size_t)(block / 32) * ring_bytes;
-  aad_encode_fast<BITS, MS><<<grid, block, smem, s>>>(p);
+  aad_encode_fast<BITS, MS, PAIR><<<grid, block, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
 
 template <int BITS>
 int enc_fast_launch(const aadk_encode_params &p, cudaStream_t s)
 {
-  if (p.geo.ms && p.geo.channels >= 2) return enc_fast_launch_as<BITS, 1>(p, s);
-  return enc_fast_launch_as<BITS, 0>(p, s);
+  /* up to one warp per scheduler (148 SMs x 4): pair the independent dry passes inside each thread */
+  const uint64_t chains = (uint64_t)p.num_streams * p.geo.channels;
+  const bool pair = p.trials >= 1 && chains <= 148ull * 4 * 32 && g_enc_pairing != 0;
+  const bool ms = p.geo.ms && p.geo.channels >= 2;
+  if (pair) return ms ? enc_fast_launch_as<BITS, 1, 1>(p, s) : enc_fast_launch_as<BITS, 0, 1>(p, s);
+  return ms ? enc_fast_launch_as<BITS, 1, 0>(p, s) : enc_fast_launch_as<BITS, 0, 0>(p, s);
 }
 
 }  // namespace

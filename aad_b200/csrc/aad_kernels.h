@@ -84,6 +84,8 @@ int aadk_launch_interleave16(const int16_t *planar, uint64_t ch_stride, int16_t 
 uint64_t aadk_launch_count(void);
 /* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths */
 void aadk_force_generic(int on);
+/* tests / measurement: 0 = the encoder never runs two passes interleaved in one thread (default 1 = when chains are scarce) */
+void aadk_set_encoder_pairing(int on);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--trials", type=int, default=TRIALS)
     ap.add_argument("--bits", type=int, default=BITS)
     ap.add_argument("--channels", type=int, default=CHANNELS)
+    ap.add_argument("--no-pairing", action="store_true", help="encoder: never interleave two passes in one thread")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=96, help="clips in the bounded CPU-baseline sample")
@@ -217,6 +218,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     api, gpu = aad_b200.load()
+    gpu.lib.AADGpu_SetEncoderPairing(0 if args.no_pairing else 1)
     ctx = gpu.create(local)
     N, ch, n = args.clips, args.channels, args.samples
     prm = make_param(ch, RATE, args.bits, MAX_BLOCK, False, args.trials)

@@ -52,6 +52,9 @@ uint32_t AADGpu_GetMaxChannels(void);
 /* 0 (default): fast kernels wherever the shape allows, generic kernels otherwise; 1: always the
  * generic (any channel count / alignment) kernels.  Both are bit-exact; this exists for testing. */
 void AADGpu_SetKernelPath(int generic_only);
+/* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
+ * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */
+void AADGpu_SetEncoderPairing(int on);
 
 /* pinned host memory for the host entry points (plain malloc'd memory works too, slower) */
 void *AADGpu_HostAlloc(size_t bytes);

@@ -172,6 +172,39 @@ def test_batch_api_matches_oracle(product, gpu_ctx, oracle, bits, channels, ms):
         assert np.array_equal(dec[i, :, :lens[i]], want), (i, lens[i])
 
 
+@pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("channels,ms", [(1, False), (2, True), (8, False)])
+def test_encoder_pass_pairing_does_not_change_a_byte(product, gpu_ctx, oracle, bits, channels, ms):
+    """With few chains the encoder interleaves the two independent dry passes of a block in one thread
+    (enc_run_pair); with pairing off they run one after the other.  Ragged lengths (pairs of unequal
+    length in every last block), trials 1..3, two block sizes; the paired result also against the oracle."""
+    _, gpu = product
+    n_streams, n_max = 41, 4300
+    rng = np.random.default_rng(1000 + bits * 10 + channels)
+    lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+    lens[0], lens[1], lens[2], lens[3] = n_max, 3, 4, 5
+    pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+    for i in range(n_streams):
+        pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], channels, int(lens[i]), 7 * i)
+    for block in (256 * channels // (2 if channels == 8 else 1), 1024):
+        for trials in (1, 2, 3):
+            res = []
+            for pairing in (1, 0):
+                gpu.lib.AADGpu_SetEncoderPairing(pairing)
+                try:
+                    aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, block, ms, trials, num_samples=lens)
+                finally:
+                    gpu.lib.AADGpu_SetEncoderPairing(1)
+                for i in range(n_streams):
+                    aad[i, sizes[i]:] = 0
+                res.append((aad, sizes))
+            assert np.array_equal(res[0][1], res[1][1]), (block, trials)
+            assert np.array_equal(res[0][0], res[1][0]), (block, trials)
+            for i in range(0, n_streams, 5):
+                rc, want = oracle.encode(pcm[i, :, :lens[i]], 44100, bits, block, ms, trials)
+                assert rc == 0 and res[0][0][i, :res[0][1][i]].tobytes() == want, (block, trials, i)
+
+
 def test_trials_zero_and_many(product, gpu_ctx, oracle):
     _, gpu = product
     pcm = np.stack([aadtest.signal(k, 2, 7000, 5) for k in aadtest.SIGNALS])
