@@ -90,7 +90,7 @@ void AADGpu_Destroy(struct AADGpu *g)
   if (!g) return;
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
-  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut, &g->wav };
+  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut, &g->wav, &g->pcm2 };
   for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
     if (bufs[i]->ptr) cudaFree(bufs[i]->ptr);
   for (int i = 0; i < 16; i++) {
@@ -502,6 +502,101 @@ AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
     CU(copy_pcm_slice(batch, C, 0, d_pcm, pitch, pcm, s0, s1, gpu->s_out), "D2H pcm");
   }
   CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  return AAD_APIRESULT_OK;
+}
+
+/* Encode a batch and decode it back in one pass over the data (what src/main.c:275-346 does for one
+ * file, execute_reconstruction_core): per block-range slice  H2D pcm | encode | decode | D2H .aad + D2H pcm.
+ * The encoded streams never make the round trip over PCIe, and the two directions of the link are busy
+ * at the same time: ~25 GB per 12,500 ten-second clips instead of 27.7 GB half-duplex.  aad / out_sizes
+ * may be NULL when only the reconstruction is wanted. */
+AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
+                                     const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes,
+                                     int16_t *reconstructed)
+{
+  if (!gpu || !batch || !pcm || !reconstructed) return AAD_APIRESULT_INVALID_ARGUMENT;
+  struct aadf_geometry geo;
+  const AADApiResult r = check_batch(batch, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  const uint32_t N = batch->num_streams, C = geo.channels, ns = batch->num_samples;
+  if (N == 0) return AAD_APIRESULT_OK;
+  if (num_samples)
+    for (uint32_t i = 0; i < N; i++)
+      if (num_samples[i] == 0 || num_samples[i] > ns) return AAD_APIRESULT_INVALID_FORMAT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+
+  const uint32_t spb = geo.samples_per_block, bs = geo.block_size;
+  const uint32_t nblk = aadf_num_blocks(ns, spb);
+  const uint64_t pitch = round_up64(ns, 64);
+  const uint64_t astride = round_up64(aadf_stream_bytes_bound(ns, bs, spb) + 1, 128);
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm2, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)N * astride + 128)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->state, (size_t)N * C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->lens, (size_t)N * 4)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->sizes, (size_t)N * 4)) return AAD_APIRESULT_NG;
+  int16_t *d_pcm = (int16_t *)gpu->pcm.ptr, *d_out = (int16_t *)gpu->pcm2.ptr;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
+
+  CU(cudaMemsetAsync(gpu->state.ptr, 0, (size_t)N * C * AADK_STATE_WORDS * 4, gpu->s_run), "memset state");
+  CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)N * astride + 128, gpu->s_run), "memset aad");
+  if (num_samples)
+    CU(cudaMemcpyAsync(gpu->lens.ptr, num_samples, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D lengths");
+
+  struct aadk_encode_params e;
+  memset(&e, 0, sizeof(e));
+  e.pcm = d_pcm;
+  e.pcm_clip_stride = (uint64_t)C * pitch;
+  e.pcm_ch_stride = pitch;
+  e.num_samples = num_samples ? (const uint32_t *)gpu->lens.ptr : NULL;
+  e.uniform_samples = ns;
+  e.num_streams = N;
+  e.geo = geo;
+  e.sampling_rate = batch->param.sampling_rate;
+  e.trials = batch->param.num_encode_trials;
+  e.aad = d_aad;
+  e.aad_stride = astride;
+  e.out_sizes = (uint32_t *)gpu->sizes.ptr;          /* written with the first slice: the decoder's byte bounds */
+  e.state_in = (const int32_t *)gpu->state.ptr;
+  e.state_out = (int32_t *)gpu->state.ptr;
+
+  struct aadk_decode_params d;
+  memset(&d, 0, sizeof(d));
+  d.aad = d_aad;
+  d.aad_stride = astride;
+  d.sizes = (const uint32_t *)gpu->sizes.ptr;
+  d.num_streams = N;
+  d.geo = geo;
+  d.read_headers = 1;                                 /* each stream's own length, written by the encoder */
+  d.pcm = d_out;
+  d.pcm_clip_stride = (uint64_t)C * pitch;
+  d.pcm_ch_stride = pitch;
+
+  const uint32_t slices = pick_slices((uint64_t)N * C * ns * 2, nblk);
+  for (uint32_t k = 0; k < slices; k++) {
+    const uint32_t b0 = (uint32_t)((uint64_t)nblk * k / slices), b1 = (uint32_t)((uint64_t)nblk * (k + 1) / slices);
+    const uint32_t s0 = b0 * spb, s1 = (b1 * (uint64_t)spb < ns) ? b1 * spb : ns;
+    CU(copy_pcm_slice(batch, C, 1, d_pcm, pitch, (int16_t *)pcm, s0, s1, gpu->s_in), "H2D pcm");
+    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
+    e.block_begin = d.block_begin = b0;
+    e.block_end = d.block_end = b1;
+    CU((cudaError_t)aadk_launch_encode(&e, gpu->s_run), "encode kernel launch");
+    CU((cudaError_t)aadk_launch_decode(&d, gpu->s_run), "decode kernel launch");
+    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
+    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    if (aad) {
+      const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+      const size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+      CU(copy_rows(aad + off, batch->aad_stream_stride, d_aad + off, astride, end - off, N, cudaMemcpyDeviceToHost,
+                   gpu->s_out), "D2H aad");
+    }
+    CU(copy_pcm_slice(batch, C, 0, d_out, pitch, reconstructed, s0, s1, gpu->s_out), "D2H pcm");
+  }
+  CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  if (out_sizes)
+    for (uint32_t i = 0; i < N; i++)
+      out_sizes[i] = (uint32_t)aadf_stream_bytes(num_samples ? num_samples[i] : ns, C, geo.bits, bs, spb);
   return AAD_APIRESULT_OK;
 }
 

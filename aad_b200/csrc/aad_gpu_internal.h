@@ -24,7 +24,7 @@ struct AADGpu {
   int device;
   cudaStream_t s_in, s_run, s_out;
   cudaEvent_t ev_in[16], ev_run[16];
-  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav;
+  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2;
   int lut_ready;
 };
 

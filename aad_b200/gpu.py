@@ -32,7 +32,7 @@ class GpuApi:
         "AADGpu_DeviceCount", "AADGpu_Create", "AADGpu_Destroy", "AADGpu_LastError", "AADGpu_KernelLaunchCount",
         "AADGpu_SetMaxChannels", "AADGpu_GetMaxChannels", "AADGpu_HostAlloc", "AADGpu_HostFree",
         "AADGpu_StreamBytesBound", "AADGpu_StreamBytes", "AADGpu_EncodeBatchDevice", "AADGpu_DecodeBatchDevice",
-        "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
+        "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_ReconstructBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
         "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath", "AADGpu_SetEncoderPairing",
         "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16",
         "AADGpuGroup_Create", "AADGpuGroup_Destroy", "AADGpuGroup_Size", "AADGpuGroup_Device",
@@ -59,6 +59,7 @@ class GpuApi:
             "AADGpu_DecodeBatchDevice": (C.c_int, [vp, bp, vp, vp, vp, vp]),
             "AADGpu_EncodeBatch": (C.c_int, [vp, bp, vp, vp, vp, vp]),
             "AADGpu_DecodeBatch": (C.c_int, [vp, bp, vp, vp, vp]),
+            "AADGpu_ReconstructBatch": (C.c_int, [vp, bp, vp, vp, vp, vp, vp]),
             "AADGpu_SynthBatchDevice": (C.c_int, [vp, bp, u32, vp, vp]),
             "AADGpu_Deinterleave16Device": (C.c_int, [vp, vp, vp, u64, u32, u32, vp]),
             "AADGpu_Interleave16Device": (C.c_int, [vp, vp, u64, vp, u32, u32, vp]),

@@ -87,6 +87,14 @@ AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
 AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                 const uint8_t *aad, const uint32_t *sizes, int16_t *pcm);
 
+/* Encode the batch and decode it back in ONE pass over the data -- src/main.c:275-346
+ * (execute_reconstruction_core) for a whole batch: per slice H2D pcm | encode | decode | D2H .aad and
+ * D2H reconstruction, both directions of the link busy at once; the encoded streams stay in HBM between
+ * the two kernels.  aad / out_sizes may be NULL when only the reconstruction is wanted. */
+AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch,
+                                     const int16_t *pcm, const uint32_t *num_samples,
+                                     uint8_t *aad, uint32_t *out_sizes, int16_t *reconstructed);
+
 /* ---- one stream in WAV order (interleaved int16), host pointers: what `aad -e / -d / -r` call ---- */
 /* src/main.c:141-227 (execute_encode) without the host-side int32 shuffle: the 16-bit samples of a
  * WAV data chunk are copied as they are and de-interleaved on the device. */

@@ -205,6 +205,35 @@ def test_encoder_pass_pairing_does_not_change_a_byte(product, gpu_ctx, oracle, b
                 assert rc == 0 and res[0][0][i, :res[0][1][i]].tobytes() == want, (block, trials, i)
 
 
+@pytest.mark.parametrize("bits,channels,ms", [(4, 1, False), (3, 2, True), (2, 8, False)])
+def test_reconstruct_batch_equals_encode_then_decode(product, gpu_ctx, bits, channels, ms):
+    """AADGpu_ReconstructBatch = AADGpu_EncodeBatch + AADGpu_DecodeBatch in one sliced pass (ragged lengths,
+    enough samples for several slices); with and without asking for the .aad."""
+    _, gpu = product
+    n_streams, n_max = 700, 30000
+    rng = np.random.default_rng(bits)
+    lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+    lens[0] = n_max
+    pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+    for i in range(n_streams):
+        pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], channels, int(lens[i]), i)
+    want_aad, want_sizes = gpu.encode_batch(gpu_ctx, pcm, 32000, bits, 1024, ms, 2, num_samples=lens)
+    want_pcm = gpu.decode_batch(gpu_ctx, want_aad, n_max, 32000, channels, bits, 1024, ms, sizes=want_sizes)
+    b = gpu.batch(n_streams, n_max, make_param(channels, 32000, bits, 1024, ms, 2))
+    for with_aad in (True, False):
+        aad = np.zeros_like(want_aad)
+        sizes = np.zeros(n_streams, dtype=np.uint32)
+        out = np.zeros_like(want_pcm)
+        rc = gpu.lib.AADGpu_ReconstructBatch(gpu_ctx, C.byref(b), pcm.ctypes.data, lens.ctypes.data,
+                                             aad.ctypes.data if with_aad else None, sizes.ctypes.data if with_aad else None,
+                                             out.ctypes.data)
+        assert rc == OK, gpu.last_error()
+        for i in range(n_streams):
+            assert np.array_equal(out[i, :, :lens[i]], want_pcm[i, :, :lens[i]]), i
+            if with_aad:
+                assert sizes[i] == want_sizes[i] and np.array_equal(aad[i, :sizes[i]], want_aad[i, :sizes[i]]), i
+
+
 def test_trials_zero_and_many(product, gpu_ctx, oracle):
     _, gpu = product
     pcm = np.stack([aadtest.signal(k, 2, 7000, 5) for k in aadtest.SIGNALS])
