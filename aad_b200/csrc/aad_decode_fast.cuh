@@ -72,7 +72,10 @@ __device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const Dec
 {
   constexpr uint32_t kMag2Mask = (1u << BITS) - 2u;          /* 2 * magnitude */
   const int32_t step = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(t.step) + c.idx2);
-  const uint32_t u = ((POS >= 1) ? (v >> (POS >= 1 ? POS - 1 : 0)) : (v << 1)) & kMag2Mask;
+  uint32_t u = ((POS >= 1) ? (v >> (POS >= 1 ? POS - 1 : 0)) : (v << 1)) & kMag2Mask;
+  /* keep u opaque: the delta-table offset below is then one multiply-add (u * 64 + base) on the FMA pipe
+   * instead of a second shift + mask of v on the ALU pipe, which is the one this kernel saturates */
+  asm("" : "+r"(u));
   const bool neg = (v & (1u << (POS + BITS - 1))) != 0u;
   const int32_t qa = (int32_t)(step * u + step) >> (BITS - 1);   /* step * (2*mag + 1) */
   const int32_t q = neg ? -qa : qa;
