@@ -37,9 +37,9 @@ METRIC = "encode+decode round-trip throughput (bit-exact AAD ADPCM)"
 UNIT = "Msamples/s"
 RATE, CLIP_SAMPLES, CHANNELS, BITS, MAX_BLOCK, TRIALS = 44100, 441000, 1, 4, 1024, 2
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel
-# (aad_encode_fast<4,0>) at the default workload: profiles/r01_v5_encode.md.  Reported only for
+# (aad_encode_fast<4,0>) at the default workload: profiles/r01_v6_encode.md.  Reported only for
 # that exact workload.
-NCU_TRAFFIC_BYTES = 35.5e9
+NCU_TRAFFIC_BYTES = 23.5e9
 
 
 def parse_args():
@@ -397,7 +397,7 @@ def run_b200_arm(args):
                          "traffic": NCU_TRAFFIC_BYTES if default_workload and dominant == "aad_encode" else None,
                          "algorithmic_bytes_per_launch": round(samples_per_step * bytes_per_sample), "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": round(bytes_per_sample, 4),
-                         "note": "12,500 serial chains per GPU: latency/issue bound, not HBM bound (DESIGN.md 4.2, profiles/r01_v5_encode.md)"},
+                         "note": "12,500 serial chains per GPU: latency/issue bound, not HBM bound (DESIGN.md 4.2, profiles/r01_v6_encode.md)"},
             "roofline_decode": {"bound": "hbm", "kernel": "aad_decode", "achieved": round(dec_gbs, 2), "peak": peak,
                                 "unit": "GB/s", "frac": round(dec_gbs / peak, 5)},
             "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
