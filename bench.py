@@ -115,13 +115,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from aad_b200.synth import synth_pcm16
-    import aad_b200
-    _, gpu = aad_b200.load()      # only for the sine table of the generator (host arithmetic)
+    from aad_b200.synth import synth_pcm16      # numpy mirror of the generator; libaad_b200.so is not loaded here
     codec = CpuCodec()
     cores = os.cpu_count() or 1
     per_step = cores * 4
-    lut = gpu.synth_lut()
+    # the generator's sine table, as AADGpu_SynthLut builds it: lrint(32767 sin(2 pi k / 1024))
+    lut = np.rint(32767.0 * np.sin(2.0 * 3.14159265358979323846 * np.arange(1024) / 1024.0)).astype(np.int16)
     clips = synth_pcm16(lut, 0, per_step, args.channels, args.samples, RATE)
 
     def one(i):
