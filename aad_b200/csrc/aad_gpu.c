@@ -73,7 +73,7 @@ struct AADGpu *AADGpu_Create(int device)
   cudaError_t e = cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking);
-  for (int i = 0; i < 16 && e == cudaSuccess; i++) {
+  for (int i = 0; i < AADGPU_MAX_SLICES && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_run[i], cudaEventDisableTiming);
   }
@@ -93,7 +93,7 @@ void AADGpu_Destroy(struct AADGpu *g)
   struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut, &g->wav, &g->pcm2 };
   for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
     if (bufs[i]->ptr) cudaFree(bufs[i]->ptr);
-  for (int i = 0; i < 16; i++) {
+  for (int i = 0; i < AADGPU_MAX_SLICES; i++) {
     if (g->ev_in[i]) cudaEventDestroy(g->ev_in[i]);
     if (g->ev_run[i]) cudaEventDestroy(g->ev_run[i]);
   }
@@ -322,12 +322,12 @@ AADApiResult AADGpu_Interleave16Device(struct AADGpu *gpu, const int16_t *planar
 
 static uint64_t round_up64(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
-/* how many block-range slices to cut the copies into: ~32 MiB of PCM each, at most 16 */
+/* how many block-range slices to cut the copies into: ~32 MiB of PCM each, at most AADGPU_MAX_SLICES */
 static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
 {
   uint64_t s = pcm_bytes / ((uint64_t)32 << 20);
   if (s < 1) s = 1;
-  if (s > 16) s = 16;
+  if (s > AADGPU_MAX_SLICES) s = AADGPU_MAX_SLICES;
   if (s > num_blocks) s = num_blocks ? num_blocks : 1;
   return (uint32_t)s;
 }

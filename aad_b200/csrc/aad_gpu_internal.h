@@ -14,6 +14,7 @@
 
 #define AADGPU_PIPE_STREAMS 3   /* H2D, kernels, D2H */
 #define AADGPU_MAX_GROUP 16     /* devices in one AADGpuGroup */
+#define AADGPU_MAX_SLICES 32    /* block-range slices a host pipeline cuts its copies into */
 
 struct aadgpu_buffer {
   void *ptr;
@@ -23,7 +24,7 @@ struct aadgpu_buffer {
 struct AADGpu {
   int device;
   cudaStream_t s_in, s_run, s_out;
-  cudaEvent_t ev_in[16], ev_run[16];
+  cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES];
   struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2;
   int lut_ready;
 };
