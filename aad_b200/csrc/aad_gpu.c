@@ -13,8 +13,10 @@
 #include "aad_gpu_internal.h"
 #include "aad_decoder.h"
 
+#include <ctype.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -131,6 +133,39 @@ void *AADGpu_HostAlloc(size_t bytes)
 void AADGpu_HostFree(void *p)
 {
   if (p) cudaFreeHost(p);
+}
+
+/* The CPUs next to the device (its PCIe root's NUMA node), from sysfs.  Host buffers a thread pins
+ * after binding itself there are allocated on that node, so the copies of one device do not cross the
+ * socket interconnect -- which is what limits a box where eight ranks pin 25 GB each. */
+int AADGpu_BindHostThread(struct AADGpu *gpu)
+{
+  char bus[32], path[128], list[1024];
+  if (!gpu) return 0;
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), gpu->device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  for (char *c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE *fp = fopen(path, "r");
+  if (!fp) return 0;
+  const int ok = fgets(list, sizeof(list), fp) != NULL;
+  fclose(fp);
+  if (!ok) return 0;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int count = 0;
+  for (const char *c = list; *c;) {          /* "0-15,32-47" */
+    if (!isdigit((unsigned char)*c)) { c++; continue; }
+    char *end;
+    long a = strtol(c, &end, 10), b = a;
+    if (*end == '-') b = strtol(end + 1, &end, 10);
+    for (long k = a; k <= b && k < CPU_SETSIZE; k++) { CPU_SET((int)k, &set); count++; }
+    c = end;
+  }
+  if (count == 0) return 0;
+  return sched_setaffinity(0, sizeof(set), &set) == 0 ? count : 0;
 }
 
 int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes)
@@ -928,6 +963,7 @@ struct group_task {
   /* GROUP_DECODE_STREAM */
   struct AADHeaderInfo header;
   uint32_t data_size, block_begin, block_end;
+  int bind;
   AADApiResult result;
   char error[320];
 };
@@ -938,6 +974,7 @@ static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHead
 static void *group_worker(void *arg)
 {
   struct group_task *t = (struct group_task *)arg;
+  if (t->bind) (void)AADGpu_BindHostThread(t->gpu);   /* a thread of its own: stay next to its device */
   switch (t->op) {
     case GROUP_ENCODE_BATCH:
       t->result = AADGpu_EncodeBatch(t->gpu, &t->batch, t->pcm_in, t->lens, t->aad_out, t->sizes_out);
@@ -958,8 +995,12 @@ static AADApiResult group_run(struct group_task *tasks, int n)
   pthread_t th[AADGPU_MAX_GROUP];
   int started[AADGPU_MAX_GROUP];
   for (int i = 0; i < n; i++) {
+    tasks[i].bind = 1;
     started[i] = pthread_create(&th[i], NULL, group_worker, &tasks[i]) == 0;
-    if (!started[i]) group_worker(&tasks[i]);    /* no thread: do it here, still correct */
+    if (!started[i]) {                           /* no thread: do it here, still correct */
+      tasks[i].bind = 0;
+      group_worker(&tasks[i]);
+    }
   }
   AADApiResult r = AAD_APIRESULT_OK;
   for (int i = 0; i < n; i++) {

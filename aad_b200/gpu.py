@@ -30,7 +30,7 @@ class AADError(RuntimeError):
 class GpuApi:
     SYMBOLS = (
         "AADGpu_DeviceCount", "AADGpu_Create", "AADGpu_Destroy", "AADGpu_LastError", "AADGpu_KernelLaunchCount",
-        "AADGpu_SetMaxChannels", "AADGpu_GetMaxChannels", "AADGpu_HostAlloc", "AADGpu_HostFree",
+        "AADGpu_SetMaxChannels", "AADGpu_GetMaxChannels", "AADGpu_HostAlloc", "AADGpu_HostFree", "AADGpu_BindHostThread",
         "AADGpu_StreamBytesBound", "AADGpu_StreamBytes", "AADGpu_EncodeBatchDevice", "AADGpu_DecodeBatchDevice",
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_ReconstructBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
         "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath", "AADGpu_SetEncoderPairing",
@@ -53,6 +53,7 @@ class GpuApi:
             "AADGpu_GetMaxChannels": (u32, []),
             "AADGpu_HostAlloc": (vp, [C.c_size_t]),
             "AADGpu_HostFree": (None, [vp]),
+            "AADGpu_BindHostThread": (C.c_int, [vp]),
             "AADGpu_StreamBytesBound": (u64, [pp, u32]),
             "AADGpu_StreamBytes": (u64, [pp, u32]),
             "AADGpu_EncodeBatchDevice": (C.c_int, [vp, bp, vp, vp, vp, vp, vp]),

@@ -220,6 +220,7 @@ def run_b200_arm(args):
     api, gpu = aad_b200.load()
     gpu.lib.AADGpu_SetEncoderPairing(0 if args.no_pairing else 1)
     ctx = gpu.create(local)
+    local_cpus = gpu.lib.AADGpu_BindHostThread(ctx)     # pinned buffers of this rank on the GPU's own NUMA node
     N, ch, n = args.clips, args.channels, args.samples
     prm = make_param(ch, RATE, args.bits, MAX_BLOCK, False, args.trials)
     batch = gpu.batch(N, n, prm)
@@ -348,7 +349,7 @@ def run_b200_arm(args):
         e2e = {"value": round(total_samples / s1 / 1e6, 3), "unit": UNIT,
                "h2d_bytes_per_step": pcm_bytes, "d2h_bytes_per_step": aad_bytes + pcm_bytes,
                "steps": e2e_steps, "ms_per_step": round(s1 * 1e3, 3), "clips_per_gpu": Ne,
-               "matches_device_resident_result": same1,
+               "matches_device_resident_result": same1, "host_cpus_bound": int(local_cpus),
                "path": "AADGpu_ReconstructBatch (host C ABI, pinned host buffers; per slice H2D pcm | encode | decode | "
                        "D2H .aad + pcm, both link directions busy at once)",
                "separate_calls": {"value": round(total_samples / s2 / 1e6, 3), "ms_per_step": round(s2 * 1e3, 3),

@@ -56,6 +56,12 @@ void AADGpu_SetKernelPath(int generic_only);
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */
 void AADGpu_SetEncoderPairing(int on);
 
+/* Bind the calling host thread to the CPUs next to the device (the NUMA node of its PCIe root, from
+ * sysfs).  Buffers the thread pins afterwards live on that node, so one device's copies do not cross
+ * the socket interconnect.  Returns the number of CPUs in the set, 0 when the topology is unknown
+ * (nothing changed).  The device-group calls do this for their own worker threads. */
+int AADGpu_BindHostThread(struct AADGpu *gpu);
+
 /* pinned host memory for the host entry points (plain malloc'd memory works too, slower) */
 void *AADGpu_HostAlloc(size_t bytes);
 void  AADGpu_HostFree(void *p);
