@@ -4,8 +4,10 @@
  * A chain = one (stream, channel).  The reference carries the predictor weights and the step
  * index from block to block (processor[], src/aad_encoder.c:21,853-886), so a chain is serial over
  * its blocks; per block it runs the start-state search (src/aad_encoder.c:470-562: 1 + 2*trials
- * dry-run passes) and then the emitting pass (src/aad_encoder.c:565-727).  One thread per chain,
- * all passes of a block through ONE copy of the sample loop (enc_run_job).
+ * dry-run passes) and then the emitting pass (src/aad_encoder.c:565-727).  One thread per chain;
+ * dry and emitting passes each have one copy of the 16-sample loop (enc_job_units<KIND>).  With few
+ * chains (PAIR = 1) the baseline pass and the first trial pass of a block, which both start from the
+ * carried state, run interleaved in the same thread (enc_run_pair).
  *
  * What makes a pass fast:
  *  - no integer divide: floor((|diff| << (b-2)) / step) is umulhi(|diff| << (b-1), M[step]) >> L[step]
@@ -23,11 +25,11 @@
  *    for the units requested after it (with plain loads the scoreboard made it so: 8 % of the
  *    v3 kernel's time, profiles/r01_v3_fast.md).
  *
- * Tried and dropped (profiles/r01_v4_encoder_experiments.md): a speculative variant that ran the
- * emitting passes next to the trial passes (second lane, or second interleaved chain in the same
+ * Tried and dropped (profiles/r01_v4_encoder_experiments.md): speculative variants that ran the
+ * EMITTING passes next to the trial passes (second lane, or second interleaved chain in the same
  * thread) to cut the critical path from 2 + 2*trials to 2*trials passes per block.  Bit-exact, but
- * not faster: it issues 8 chain-passes per block instead of 6 and a lone warp per scheduler is
- * already limited by the integer pipes' issue rate, not only by latency.
+ * not faster: they issue 8 chain-passes per block instead of 6, and each candidate start state
+ * wins about a third of the blocks, so an emission run early is wasted two times out of three.
  */
 #pragma once
 
