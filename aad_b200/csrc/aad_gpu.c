@@ -646,21 +646,24 @@ AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
   const uint64_t pitch = round_up64(num_samples, 64);
   const uint64_t bytes = aadf_stream_bytes(num_samples, C, geo->bits, geo->block_size, geo->samples_per_block);
   const uint64_t bound = aadf_stream_bytes_bound(num_samples, geo->block_size, geo->samples_per_block);
-  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;    /* int32 rows as given */
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;    /* int16 rows for the kernel */
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->state, (size_t)C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
-  int32_t *d_pcm = (int32_t *)gpu->pcm.ptr;
+  int32_t *d_in = (int32_t *)gpu->wav.ptr;
   uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
   cudaStream_t s = gpu->s_run;
   for (uint32_t c = 0; c < C; c++)
-    CU(cudaMemcpyAsync(d_pcm + c * pitch, input[c], (size_t)num_samples * 4, cudaMemcpyHostToDevice, s), "H2D pcm");
+    CU(cudaMemcpyAsync(d_in + c * pitch, input[c], (size_t)num_samples * 4, cudaMemcpyHostToDevice, s), "H2D pcm");
+  /* the reference API carries 16-bit samples in int32 (src/aad_encoder.c:451,612): narrow on the device
+   * and run the same int16 kernels as every other path */
+  CU((cudaError_t)aadk_launch_narrow32(d_in, pitch, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s), "narrow kernel launch");
   CU(cudaMemcpyAsync(gpu->state.ptr, state, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyHostToDevice, s), "H2D state");
   struct aadk_encode_params p;
   memset(&p, 0, sizeof(p));
-  p.pcm = d_pcm;
+  p.pcm = gpu->pcm.ptr;
   p.pcm_clip_stride = (uint64_t)C * pitch;
   p.pcm_ch_stride = pitch;
-  p.in32 = 1;
   p.uniform_samples = num_samples;
   p.num_streams = 1;
   p.geo = *geo;
@@ -693,9 +696,11 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
   const uint64_t pitch = round_up64(total, 64);
   uint64_t span = AADF_FILE_HEADER_BYTES + (uint64_t)num_blocks * bs;
   if (span > data_size) span = data_size;
-  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;    /* int16 rows from the kernel */
+  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;    /* int32 rows for the caller */
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 128)) return AAD_APIRESULT_NG;
-  int32_t *d_pcm = (int32_t *)gpu->pcm.ptr;
+  int16_t *d_pcm = (int16_t *)gpu->pcm.ptr;
+  int32_t *d_out = (int32_t *)gpu->wav.ptr;
   uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
 
   struct aadk_decode_params p;
@@ -710,7 +715,6 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
   p.pcm = d_pcm;
   p.pcm_clip_stride = (uint64_t)C * pitch;
   p.pcm_ch_stride = pitch;
-  p.out32 = 1;
 
   const uint32_t slices = pick_slices(total * C * 4, num_blocks);
   for (uint32_t k = 0; k < slices; k++) {
@@ -726,10 +730,12 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
     p.block_begin = b0;
     p.block_end = b1;
     CU((cudaError_t)aadk_launch_decode(&p, gpu->s_run), "decode kernel launch");
+    if (s1 > s0)   /* widen to the API's sample type on the device */
+      CU((cudaError_t)aadk_launch_widen16(d_pcm, pitch, d_out, pitch, C, s0, s1 - s0, gpu->s_run), "widen kernel launch");
     CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
     CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
     for (uint32_t c = 0; c < C && s1 > s0; c++)
-      CU(cudaMemcpyAsync(buffer[c] + s0, d_pcm + c * pitch + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost,
+      CU(cudaMemcpyAsync(buffer[c] + s0, d_out + c * pitch + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost,
                          gpu->s_out), "D2H pcm");
   }
   CU(cudaStreamSynchronize(gpu->s_out), "sync");

@@ -434,6 +434,27 @@ __global__ void aad_interleave16(const int16_t *__restrict__ in, uint64_t ch_str
   out[t] = in[(uint64_t)c * ch_stride + s];
 }
 
+/* int32 <-> int16 planar rows: the reference API carries 16-bit PCM in int32_t (src/aad_encoder.h:47-50,
+ * asserted at src/aad_encoder.c:451,612); the production kernels work on int16.  rows x n elements, row
+ * pitches in elements. */
+__global__ void aad_narrow32(const int32_t *__restrict__ in, uint64_t in_pitch, int16_t *__restrict__ out,
+                             uint64_t out_pitch, uint32_t rows, uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)rows * n) return;
+  const uint64_t r = t / n, i = t % n;
+  out[r * out_pitch + i] = (int16_t)in[r * in_pitch + i];
+}
+
+__global__ void aad_widen16(const int16_t *__restrict__ in, uint64_t in_pitch, int32_t *__restrict__ out,
+                            uint64_t out_pitch, uint32_t rows, uint64_t first, uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)rows * n) return;
+  const uint64_t r = t / n, i = first + t % n;
+  out[r * out_pitch + i] = (int32_t)in[r * in_pitch + i];
+}
+
 inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
 }  // namespace
@@ -523,6 +544,24 @@ int aadk_launch_deinterleave16(const int16_t *interleaved, int16_t *planar, uint
   if (n == 0) return 0;
   aad_deinterleave16<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(interleaved, planar, ch_stride, channels,
                                                                          num_samples);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_narrow32(const int32_t *in, uint64_t in_pitch, int16_t *out, uint64_t out_pitch, uint32_t rows, uint64_t n,
+                         void *stream)
+{
+  if ((uint64_t)rows * n == 0) return 0;
+  aad_narrow32<<<grid_for((uint64_t)rows * n, 256), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, n);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_widen16(const int16_t *in, uint64_t in_pitch, int32_t *out, uint64_t out_pitch, uint32_t rows, uint64_t first,
+                        uint64_t n, void *stream)
+{
+  if ((uint64_t)rows * n == 0) return 0;
+  aad_widen16<<<grid_for((uint64_t)rows * n, 256), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, first, n);
   g_launches++;
   return (int)cudaGetLastError();
 }

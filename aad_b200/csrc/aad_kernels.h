@@ -80,6 +80,13 @@ int aadk_launch_deinterleave16(const int16_t *interleaved, int16_t *planar, uint
 int aadk_launch_interleave16(const int16_t *planar, uint64_t ch_stride, int16_t *interleaved, uint32_t channels,
                              uint32_t num_samples, void *stream);
 
+/* planar int32 rows (the reference API's sample type, int16-range values) <-> planar int16 rows;
+ * pitches in elements; widen converts elements [first, first + n) of every row */
+int aadk_launch_narrow32(const int32_t *in, uint64_t in_pitch, int16_t *out, uint64_t out_pitch, uint32_t rows, uint64_t n,
+                         void *stream);
+int aadk_launch_widen16(const int16_t *in, uint64_t in_pitch, int32_t *out, uint64_t out_pitch, uint32_t rows, uint64_t first,
+                        uint64_t n, void *stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t aadk_launch_count(void);
 /* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths */
