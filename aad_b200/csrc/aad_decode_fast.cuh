@@ -359,7 +359,6 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
 
 inline bool dec_fast_eligible(const aadk_decode_params &p)
 {
-  if (p.out32) return false;
   if (p.geo.channels != 1 && p.geo.channels != 2) return false;
   if (p.geo.samples_per_block % 4u) return false;
   if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u)) return false;

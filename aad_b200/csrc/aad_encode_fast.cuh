@@ -633,7 +633,6 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
 /* rows must be 8-byte aligned wherever a unit is staged */
 inline bool enc_fast_eligible(const aadk_encode_params &p)
 {
-  if (p.in32) return false;
   if (p.geo.samples_per_block % 4u) return false;
   if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u)) return false;
   return true;

@@ -176,11 +176,8 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
 
   const uint64_t out_base = stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
   int16_t *out16 = (int16_t *)p.pcm + out_base;
-  int32_t *out32 = (int32_t *)p.pcm + out_base;
   auto put = [&](uint32_t i, int32_t v) {
-    if (i < want) {
-      if (p.out32) out32[i] = v; else out16[i] = (int16_t)v;
-    }
+    if (i < want) out16[i] = (int16_t)v;
   };
 #pragma unroll
   for (int i = 0; i < 4; i++) put(i, c.h[3 - i]);
@@ -200,7 +197,7 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
   }
 }
 
-/* mid/side -> left/right over decoded output (src/aad_decoder.c:458-470), generic path only */
+/* mid/side -> left/right over decoded output (src/aad_decoder.c:458-470); follows either decoder */
 __global__ void aad_ms_to_lr(const aadk_decode_params p)
 {
   const uint32_t spb = p.geo.samples_per_block;
@@ -222,40 +219,28 @@ __global__ void aad_ms_to_lr(const aadk_decode_params p)
   if (s >= buf) return;
   const uint64_t i0 = stream * p.pcm_clip_stride + s;
   const uint64_t i1 = i0 + p.pcm_ch_stride;
-  if (p.out32) {
-    int32_t *o = (int32_t *)p.pcm;
-    const int32_t m = o[i0], d = o[i1];
-    o[i0] = clamp16(m + d);
-    o[i1] = clamp16(m - d);
-  } else {
-    int16_t *o = (int16_t *)p.pcm;
-    const int32_t m = o[i0], d = o[i1];
-    o[i0] = (int16_t)clamp16(m + d);
-    o[i1] = (int16_t)clamp16(m - d);
-  }
+  int16_t *o = (int16_t *)p.pcm;
+  const int32_t m = o[i0], d = o[i1];
+  o[i0] = (int16_t)clamp16(m + d);
+  o[i1] = (int16_t)clamp16(m - d);
 }
 
 /* ------------------------------------------------------------------------------------------
  * encode, generic path.
  * ------------------------------------------------------------------------------------------ */
 
-/* Sample source for one (stream, channel): int16 or int32 planar PCM, optional LR->MS on the
+/* Sample source for one (stream, channel): int16 planar PCM, optional LR->MS on the
  * fly (src/aad_encoder.c:413-428), zero beyond `limit` (src/aad_encoder.c:592-593). */
 struct SampleSource {
   const int16_t *a16, *b16;
-  const int32_t *a32, *b32;
   int mode; /* 0 plain, 1 mid, 2 side */
 
-  __device__ __forceinline__ int32_t raw(const int16_t *p16, const int32_t *p32, uint32_t i) const
-  {
-    return p32 ? (int32_t)(int16_t)p32[i] : (int32_t)p16[i];
-  }
   __device__ __forceinline__ int32_t at(uint32_t i, uint32_t limit) const
   {
     if (i >= limit) return 0;
-    const int32_t x = raw(a16, a32, i);
+    const int32_t x = a16[i];
     if (mode == 0) return x;
-    const int32_t y = raw(b16, b32, i);
+    const int32_t y = b16[i];
     return clamp16(mode == 1 ? (x + y) >> 1 : (x - y) >> 1);
   }
 };
@@ -308,10 +293,8 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
     const bool ms = p.geo.ms && C >= 2 && ch < 2;
     const uint64_t off_a = base + (uint64_t)(ms ? 0 : ch) * p.pcm_ch_stride;
     const uint64_t off_b = base + p.pcm_ch_stride;
-    src.a16 = p.in32 ? nullptr : (const int16_t *)p.pcm + off_a;
-    src.b16 = p.in32 ? nullptr : (const int16_t *)p.pcm + off_b;
-    src.a32 = p.in32 ? (const int32_t *)p.pcm + off_a : nullptr;
-    src.b32 = p.in32 ? (const int32_t *)p.pcm + off_b : nullptr;
+    src.a16 = (const int16_t *)p.pcm + off_a;
+    src.b16 = (const int16_t *)p.pcm + off_b;
     src.mode = ms ? (ch == 0 ? 1 : 2) : 0;
   }
 

@@ -30,17 +30,15 @@ struct aadk_decode_params {
   uint32_t uniform_samples;    /* samples per channel when read_headers == 0 */
   uint32_t read_headers;       /* 1: take num_samples from each stream's own 31-byte header */
   uint32_t buf_samples;        /* output capacity per channel (reference DecodeWhole semantics); 0 = num_samples */
-  void *pcm;                   /* planar: sample s of channel c of stream i at i*clip_stride + c*ch_stride + s */
+  void *pcm;                   /* planar int16: sample s of channel c of stream i at i*clip_stride + c*ch_stride + s */
   uint64_t pcm_clip_stride;    /* in samples */
   uint64_t pcm_ch_stride;      /* in samples */
-  uint32_t out32;              /* 0: int16 samples, 1: int32 samples (the reference API type) */
 };
 
 struct aadk_encode_params {
-  const void *pcm;             /* planar, same addressing as the decoder's output */
+  const void *pcm;             /* planar int16, same addressing as the decoder's output */
   uint64_t pcm_clip_stride;
   uint64_t pcm_ch_stride;
-  uint32_t in32;               /* 0: int16 samples, 1: int32 samples holding int16-range values */
   const uint32_t *num_samples; /* per stream, or NULL -> uniform_samples */
   uint32_t uniform_samples;
   uint32_t num_streams;
