@@ -282,6 +282,23 @@ def run_b200_arm(args):
     ms_per_step = total_ms / args.steps
     value = samples_per_step * world / (ms_per_step * 1e-3) / 1e6
 
+    # ---- the encoder without the start-state search (num_encode_trials = 0: one pass per block), for
+    #      reference next to the CLI-default setting the headline uses --------------------
+    trials0 = None
+    if args.trials != 0:
+        b0 = gpu.batch(N, n, make_param(ch, RATE, args.bits, MAX_BLOCK, False, 0))
+        scratch = torch.zeros_like(aad)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for k in range(2):      # first launch warms up
+            evs[0].record()
+            check(gpu.lib.AADGpu_EncodeBatchDevice(ctx, C.byref(b0), pcm.data_ptr(), None, scratch.data_ptr(), None, stream), "encode t0")
+            evs[1].record()
+        torch.cuda.synchronize()
+        ms0 = evs[0].elapsed_time(evs[1])
+        trials0 = {"kernel_ms": round(ms0, 3), "encode_msamples_s": round(samples_per_step / (ms0 * 1e-3) / 1e6, 3),
+                   "hbm_frac": round(samples_per_step * bytes_per_sample / (ms0 * 1e-3) / 1e9 / hbm_peak()[0], 5)}
+        del scratch
+
     # ---- end to end through the host C ABI, pinned host buffers ------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -400,6 +417,7 @@ def run_b200_arm(args):
                          "note": "12,500 serial chains per GPU: latency/issue bound, not HBM bound (DESIGN.md 4.2, profiles/r01_v6_encode.md)"},
             "roofline_decode": {"bound": "hbm", "kernel": "aad_decode", "achieved": round(dec_gbs, 2), "peak": peak,
                                 "unit": "GB/s", "frac": round(dec_gbs / peak, 5)},
+            "encode_without_search": trials0,
             "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
