@@ -357,9 +357,224 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
   }
 }
 
+/*
+ * aad_decode_wide<BITS> -- the same staged data path for any channel count up to 32 (run time C):
+ * the multichannel streams of BASELINE config 4 (8 channels, 3-bit).  A warp owns floor(32 / C)
+ * consecutive blocks, lane = (block row, channel); the lanes past rows * C idle.  Windows are the
+ * same 128 samples per chain (16 * BITS * C input bytes per block).  A block interleaves the
+ * channels group by group (src/aad_decoder.c:394-455), so a chain's codes are GB bytes every
+ * GB * C bytes: each lane picks its own bytes out of the shared input row (the lanes of a row read
+ * neighbouring bytes of the same words, the rows sit 4 banks apart or more) -- byte reads instead
+ * of the mono / stereo kernel's sliding words, everything else as there: 16-byte coalesced global
+ * loads one window ahead, 8-byte shared output stores, coalesced 8-byte row stores to the PCM planes.
+ */
+template <int BITS>
+__global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_decode_params p)
+{
+  constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
+  constexpr uint32_t GS = (BITS == 4) ? 2 : (BITS == 3 ? 8 : 4);
+  constexpr int kLoads = BITS + 1;          /* ceil(rows * chunks / 32) <= BITS + 1 for every C */
+  extern __shared__ __align__(16) unsigned char dec_smem[];
+  DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
+  dec_load_tables<BITS>(tab);
+
+  const uint32_t C = p.geo.channels;
+  const uint32_t rows = 32u / C, active = rows * C;
+  const uint32_t TB = 16u * BITS * C;                  /* input bytes per block per window */
+  const uint32_t chunks = BITS * C + 1u;               /* 16-byte chunks per row: aligned superset */
+  const uint32_t pitch = 16u * chunks;
+  const uint32_t in_bytes = (rows * pitch + 16u + 15u) & ~15u;
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * (in_bytes + 32u * kDecOutPitch);
+  unsigned char *out_rows = in_rows + in_bytes;
+  const int *dl = &tab.delta2[0][lane];
+
+  const uint32_t spb = p.geo.samples_per_block;
+  const uint32_t bs = p.geo.block_size;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint32_t warps_per_stream = (nblocks + rows - 1) / rows;
+  const uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp;
+  const uint64_t stream = gw / warps_per_stream;
+  if (stream >= p.num_streams) return;                      /* whole warp */
+  const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * rows;
+
+  const uint8_t *slot = p.aad + stream * p.aad_stride;
+  const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
+  uint32_t ns = p.uniform_samples;
+  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+
+  /* this lane's chain (idle lanes shadow row 0 and deliver nothing) */
+  const bool lane_on = lane < active;
+  const uint32_t row = lane_on ? lane / C : 0u, ch = lane_on ? lane % C : 0u;
+  const uint32_t b = b0 + row;
+  const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+  const bool have = lane_on && b < p.block_end && (uint64_t)b * spb < ns &&
+                    blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
+  const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;
+  int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+  int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;
+  const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb || !lane_on);
+
+  /* loader role */
+  const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
+  const uint8_t *ld_ptr[kLoads];
+  uint32_t ld_smem[kLoads];
+#pragma unroll
+  for (int m = 0; m < kLoads; m++) {
+    const uint32_t f = lane + 32u * m;
+    const uint32_t rr = f / chunks, cc = f % chunks;
+    const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
+    ld_ptr[m] = (f < rows * chunks) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
+    ld_smem[m] = rr * pitch + 16u * cc;
+  }
+  const uint8_t *slot_end = slot + size;
+  auto fetch = [&](int m) -> uint4 {
+    const uint8_t *q = ld_ptr[m];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (q == nullptr || q >= slot_end) return v;
+    if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
+    unsigned char tmp[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past the data read as zero */
+    v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
+    v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
+    v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
+    v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+    return v;
+  };
+
+  /* reader role */
+  const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
+  const unsigned char *irow = in_rows + row * pitch + a_r;
+  unsigned char *orow = out_rows + lane * kDecOutPitch;
+
+  DecChain c;
+  c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+
+  const uint32_t windows = (bs + TB - 1) / TB;
+  const uint32_t gstride = GB * C;
+  uint4 pre[kLoads];
+#pragma unroll
+  for (int m = 0; m < kLoads; m++) pre[m] = fetch(m);
+
+  uint32_t out_base = 0;
+  for (uint32_t w = 0; w < windows; w++) {
+#pragma unroll
+    for (int m = 0; m < kLoads; m++)
+      if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
+    __syncwarp();
+    if (w + 1 < windows) {
+#pragma unroll
+      for (int m = 0; m < kLoads; m++) {
+        if (ld_ptr[m] != nullptr) ld_ptr[m] += TB;
+        pre[m] = fetch(m);
+      }
+    }
+
+    uint32_t produced = 0;
+    uint32_t pos = 0;
+    if (w == 0) {   /* block header, src/aad_decoder.c:364-391 */
+      const unsigned char *hp = irow + AADF_CHANNEL_HEADER_BYTES * ch;
+      const uint32_t head = ((uint32_t)hp[0] << 8) | hp[1];
+      c.idx2 = 2 * (int32_t)(int16_t)(head >> 4);
+      c.idx2 = max(0, min(c.idx2, 2 * AADF_INDEX_MAX));
+      const uint32_t shift = head & 0xFu;
+      int32_t wv[4], hv[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)(((uint32_t)hp[2 + 4 * k] << 8) | hp[3 + 4 * k]) << shift);
+        hv[k] = (int32_t)(int16_t)(((uint32_t)hp[4 + 4 * k] << 8) | hp[5 + 4 * k]);
+      }
+      c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
+      c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
+      const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };
+      dec_emit<4>(orow, 0, first4);
+      produced = 4;
+      pos = AADF_CHANNEL_HEADER_BYTES * C;
+    }
+
+    /* this chain's groups of the window: GB bytes every GB * C bytes; 4 (2-bit, 4-bit) or 8 (3-bit)
+     * samples per turn so the shared output row takes whole 8-byte pieces */
+    {
+      const unsigned char *bp = irow + pos + GB * ch;
+      const uint32_t groups = (TB - pos) / gstride;          /* even for 4-bit in every window */
+      if (BITS == 4) {
+#pragma unroll 2
+        for (uint32_t g = 0; g < groups; g += 2) {
+          const uint32_t v = (uint32_t)bp[0] | ((uint32_t)bp[gstride] << 8);
+          bp += 2u * gstride;
+          int32_t o[4];
+          dec_byte<4, 0>(c, v, tab, dl, o);
+          dec_byte<4, 1>(c, v, tab, dl, o + 2);
+          dec_emit<4>(orow, produced, o);
+          produced += 4;
+        }
+      } else if (BITS == 3) {
+#pragma unroll 2
+        for (uint32_t g = 0; g < groups; g++) {
+          const uint32_t v = ((uint32_t)bp[0] << 16) | ((uint32_t)bp[1] << 8) | bp[2];
+          bp += gstride;
+          int32_t o[8];
+          dec_group3(c, v, tab, dl, o);
+          dec_emit<8>(orow, produced, o);
+          produced += 8;
+        }
+      } else {
+#pragma unroll 2
+        for (uint32_t g = 0; g < groups; g++) {
+          const uint32_t v = bp[0];
+          bp += gstride;
+          int32_t o[4];
+          dec_byte<2, 0>(c, v, tab, dl, o);
+          dec_emit<4>(orow, produced, o);
+          produced += 4;
+        }
+      }
+    }
+    __syncwarp();
+
+    /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
+    if (all_full) {
+      if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+        const unsigned char *srow = out_rows + 8u * lane;
+        int16_t *dst_blk = grow0 + out_base + 4u * lane;
+        int16_t *dst = dst_blk;
+        uint32_t rch = 0;
+#pragma unroll 4
+        for (uint32_t rr = 0; rr < active; rr++) {
+          *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+          dst += p.pcm_ch_stride;
+          if (++rch == C) { rch = 0; dst_blk += spb; dst = dst_blk; }
+        }
+      }
+    } else {
+      for (uint32_t rr = 0; rr < active; rr++) {
+        const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+        const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+        const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+        if (n_rr <= out_base) continue;                       /* uniform */
+        const uint32_t count = min(made, n_rr - out_base);
+        int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+        const unsigned char *srow = out_rows + rr * kDecOutPitch;
+        const uint32_t s0 = lane * 4u;
+        if (s0 + 4u <= count) {
+          *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+        } else {
+          for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+        }
+      }
+    }
+    out_base += produced;       /* identical in every lane */
+    __syncwarp();
+  }
+}
+
 inline bool dec_fast_eligible(const aadk_decode_params &p)
 {
-  if (p.geo.channels != 1 && p.geo.channels != 2) return false;
+  if (p.geo.channels < 1 || p.geo.channels > 32) return false;
   if (p.geo.samples_per_block % 4u) return false;
   if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u)) return false;
   /* the window arithmetic assumes the canonical block layout: header, then whole groups */
@@ -386,8 +601,25 @@ int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
 }
 
 template <int BITS>
+int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
+{
+  const uint32_t C = p.geo.channels, rows = 32u / C;
+  const size_t in_bytes = ((size_t)rows * 16u * (BITS * C + 1u) + 16u + 15u) & ~(size_t)15;
+  const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (in_bytes + 32u * kDecOutPitch);
+  cudaError_t e = cudaFuncSetAttribute(aad_decode_wide<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + rows - 1) / rows);
+  const unsigned grid = (unsigned)((warps + kDecWarps - 1) / kDecWarps);
+  aad_decode_wide<BITS><<<grid, kDecWarps * 32, smem, s>>>(p);
+  return (int)cudaGetLastError();
+}
+
+/* g_dec_wide_all (tests): 1 = mono and stereo streams also go through aad_decode_wide */
+template <int BITS>
 int dec_fast_launch(const aadk_decode_params &p, cudaStream_t s)
 {
+  if (p.geo.channels > 2 || g_dec_wide_all) return dec_wide_launch<BITS>(p, s);
   return p.geo.channels == 1 ? dec_fast_launch_bc<BITS, 1>(p, s) : dec_fast_launch_bc<BITS, 2>(p, s);
 }
 

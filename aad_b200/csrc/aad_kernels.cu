@@ -27,6 +27,7 @@ __device__ const int16_t g_delta4[8] = AADK_DELTA4_INIT;
 
 unsigned long long g_launches = 0;
 int g_force_generic = 0;   /* tests: route everything through the generic kernels */
+int g_dec_wide_all = 0;    /* tests: mono / stereo decode through the any-channel-count staged kernel too */
 int g_enc_pairing = 1;     /* tests / measurement: 0 = never pair the independent dry passes */
 
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
@@ -448,7 +449,7 @@ inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((
 extern "C" {
 
 uint64_t aadk_launch_count(void) { return g_launches; }
-void aadk_force_generic(int on) { g_force_generic = on; }
+void aadk_force_generic(int on) { g_force_generic = (on == 1); g_dec_wide_all = (on == 2); }
 void aadk_set_encoder_pairing(int on) { g_enc_pairing = on ? 1 : 0; }
 
 int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)

@@ -87,7 +87,8 @@ int aadk_launch_widen16(const int16_t *in, uint64_t in_pitch, int32_t *out, uint
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t aadk_launch_count(void);
-/* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths */
+/* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths;
+ * 2 = decode mono / stereo streams with the any-channel-count staged kernel (aad_decode_wide) too */
 void aadk_force_generic(int on);
 /* tests / measurement: 0 = the encoder never runs two passes interleaved in one thread (default 1 = when chains are scarce) */
 void aadk_set_encoder_pairing(int on);

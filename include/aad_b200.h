@@ -49,9 +49,11 @@ const char *AADGpu_LastError(void);                      /* thread-local, never 
 uint64_t AADGpu_KernelLaunchCount(void);                 /* kernels launched by this library so far */
 void AADGpu_SetMaxChannels(uint32_t max_channels);       /* 2 = stock reference limit, 8 = default */
 uint32_t AADGpu_GetMaxChannels(void);
-/* 0 (default): fast kernels wherever the shape allows, generic kernels otherwise; 1: always the
- * generic (any channel count / alignment) kernels.  Both are bit-exact; this exists for testing. */
-void AADGpu_SetKernelPath(int generic_only);
+/* 0 (default): fast kernels wherever the shape allows (mono / stereo: aad_decode_fast, 3..8 channels:
+ * aad_decode_wide), generic kernels otherwise; 1: always the generic (any channel count / alignment)
+ * kernels; 2: like 0, but mono / stereo streams are decoded by aad_decode_wide too.  All bit-exact;
+ * this exists for testing. */
+void AADGpu_SetKernelPath(int path);
 /* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */
 void AADGpu_SetEncoderPairing(int on);

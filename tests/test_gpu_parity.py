@@ -100,6 +100,49 @@ def test_fast_and_generic_kernels_agree(product, gpu_ctx, bits, channels):
         assert np.array_equal(res[0][2], res[1][2]), (bits, channels, block)
 
 
+@pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("channels", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_wide_decoder_agrees_with_generic_and_oracle(product, gpu_ctx, oracle, bits, channels):
+    """aad_decode_wide (any channel count, staged through shared memory; mono / stereo forced onto it with
+    kernel path 2) against the generic decoder on ragged batches and several block sizes, MS on and off,
+    truncated streams; a sample of streams also against the oracle."""
+    _, gpu = product
+    rng = np.random.default_rng(300 + bits + 10 * channels)
+    for block in (32 * channels, 128 * channels, 1024, 4096):
+        for ms in ((False, True) if channels >= 2 else (False,)):
+            n_streams, n_max = 45, 7000
+            _, bs, spb = oracle.geometry(block, channels, bits)
+            lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+            lens[0], lens[1], lens[2] = n_max, 4, 5
+            pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+            for i in range(n_streams):
+                pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], channels, int(lens[i]), 90 + i)
+            aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 48000, bits, block, ms, 1, num_samples=lens)
+            cut = sizes.copy()                      # truncate a few streams inside / at the edge of a block
+            for i in range(3, n_streams, 7):
+                cut[i] = max(31, int(sizes[i]) - int(rng.integers(0, 2 * block)))
+            res = []
+            for path in (2, 1):
+                gpu.lib.AADGpu_SetKernelPath(path)
+                try:
+                    full = gpu.decode_batch(gpu_ctx, aad, n_max, 48000, channels, bits, block, ms, sizes=sizes)
+                    part = gpu.decode_batch(gpu_ctx, aad, n_max, 48000, channels, bits, block, ms, sizes=cut)
+                finally:
+                    gpu.lib.AADGpu_SetKernelPath(0)
+                for i in range(n_streams):
+                    full[i, :, lens[i]:] = 0
+                    # a block is decoded when all of its channel headers are present (src/aad_decoder.c:347);
+                    # what lies behind the last such block is not part of the result
+                    nb = (int(cut[i]) - 31 - 18 * channels) // bs + 1 if cut[i] >= 31 + 18 * channels else 0
+                    part[i, :, min(int(lens[i]), nb * spb):] = 0
+                res.append((full, part))
+            assert np.array_equal(res[0][0], res[1][0]), (bits, channels, block, ms)
+            assert np.array_equal(res[0][1], res[1][1]), (bits, channels, block, ms)
+            for i in range(0, n_streams, 9):
+                _, want, _ = oracle.decode(aad[i, :sizes[i]].tobytes())
+                assert np.array_equal(res[0][0][i, :, :lens[i]], want), (bits, channels, block, ms, i)
+
+
 def test_five_bits_is_rejected_like_the_reference(product, gpu_ctx):
     api, gpu = product
     pcm = aadtest.signal("sine", 1, 500)
