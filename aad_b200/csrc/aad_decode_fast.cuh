@@ -21,14 +21,45 @@
 
 namespace {
 
-constexpr int kDecWarps = 4;
+#ifndef AAD_DEC_WARPS
+#define AAD_DEC_WARPS 16
+#endif
+constexpr int kDecWarps = AAD_DEC_WARPS;
 constexpr int kDecWindow = 128;           /* samples per chain per window */
 constexpr int kDecOutPitch = 264;         /* 256 + 8: conflict-free 8-byte shared accesses */
 
+#ifndef AAD_DEC_QTAB
+#define AAD_DEC_QTAB 1
+#endif
+
+#if AAD_DEC_QTAB
+/* Dequantised difference per (step row, code) and index delta per magnitude, both in shared memory.
+ * The chain keeps J = 4 * stepsize_index; the row of src/aad_tables.h:41 ((index + 8) >> 4) starts at byte
+ * (J + 32) & ~63, and a code shifted to bits 2..5 selects the entry: one LOP3 builds the address, one
+ * LDS returns +-((step * (2 mag + 1)) >> (bits - 1)) (src/aad_decoder.c:284-296) -- no multiply, shift, sign
+ * test or negate per sample.  Rows hold 16 entries for every bit depth (entry e = code e mod 2^bits), so
+ * the bits above a narrower code need no masking.  The 8 deltas sit in 8 different banks: lanes either
+ * read the same word (broadcast) or different banks, never a conflict. */
+#if AAD_DEC_QTAB == 2
+/* rows per HALF step (index >> 3; (index + 8) >> 4 == ((index >> 3) + 1) >> 1): the chain keeps 8 * index and the
+ * row address needs no rounding add */
+constexpr int kDecRows = 511;
+constexpr int kDecIdxScale = 8;
+#else
+constexpr int kDecRows = 256;
+constexpr int kDecIdxScale = 1;
+#endif
+struct DecTables {
+  int32_t q[kDecRows][16];
+  int32_t delta4[8];                      /* kDecIdxScale * index delta per magnitude code */
+};
+#else
 struct DecTables {
   uint16_t step[kEncLutEntries + 7];      /* step[stepsize_index] */
   int delta2[8][32];                      /* 2 * index delta per magnitude code, one column per lane */
 };
+constexpr int kDecIdxScale = 2;
+#endif
 
 template <int BITS, int C>
 struct DecGeom {
@@ -45,6 +76,28 @@ struct DecGeom {
   static constexpr int WARP_BYTES = ((IN_BYTES + 15) & ~15) + 32 * kDecOutPitch;
 };
 
+#if AAD_DEC_QTAB
+template <int BITS>
+__device__ __forceinline__ void dec_load_tables(DecTables &t)
+{
+  for (int i = threadIdx.x; i < kDecRows * 16; i += blockDim.x) {
+    const int32_t step = g_step_table[AAD_DEC_QTAB == 2 ? ((i >> 4) + 1) >> 1 : i >> 4];
+    const int code = i & ((1 << BITS) - 1);
+    const int mag = code & ((1 << (BITS - 1)) - 1);
+    const int32_t qa = (step * (2 * mag + 1)) >> (BITS - 1);
+    t.q[i >> 4][i & 15] = (code >> (BITS - 1)) ? -qa : qa;
+  }
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x;
+    int d = 0;
+    if (BITS == 4) d = g_delta4[k];
+    if (BITS == 3) d = g_delta3[k & 3];
+    if (BITS == 2) d = g_delta2[k & 1];
+    t.delta4[k] = kDecIdxScale * d;
+  }
+  __syncthreads();
+}
+#else
 template <int BITS>
 __device__ __forceinline__ void dec_load_tables(DecTables &t)
 {
@@ -60,12 +113,47 @@ __device__ __forceinline__ void dec_load_tables(DecTables &t)
   __syncthreads();
 }
 
+#endif
+
 struct DecChain {
   int32_t h0, h1, h2, h3;
   int32_t w0, w1, w2, w3;
-  int32_t idx2;   /* 2 * stepsize_index = byte offset into DecTables::step */
+  int32_t idx2;   /* kDecIdxScale * stepsize_index */
 };
 
+#if AAD_DEC_QTAB
+/* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
+template <int BITS, int POS>
+__device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t, const int *)
+{
+  constexpr uint32_t kMagField = ((1u << (BITS - 1)) - 1u) << 2;
+  const uint32_t x = (POS >= 2) ? (v >> (POS >= 2 ? POS - 2 : 0)) : (v << (POS >= 2 ? 0 : 2 - POS));   /* code at bits 2.. */
+#if AAD_DEC_QTAB == 2
+  const uint32_t row = (uint32_t)c.idx2;
+#else
+  uint32_t row;    /* 4 * (index + 8) on the multiply pipe (the ALU pipe is the one this kernel saturates) */
+  asm("mad.lo.u32 %0, %1, 4, 32;" : "=r"(row) : "r"(c.idx2));
+#endif
+  uint32_t qoff;   /* (row & ~0x3C) | (x & 0x3C); bits 0-1 of row are zero */
+  asm("lop3.b32 %0, %1, %2, 0x3C, 0xD8;" : "=r"(qoff) : "r"(row), "r"(x));
+  const int32_t q = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.q) + qoff);
+  const int32_t d = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.delta4) + (x & kMagField));
+  const uint32_t acc = (1u << 14) + (uint32_t)c.h0 * (uint32_t)c.w0 + (uint32_t)c.h1 * (uint32_t)c.w1 +
+                       (uint32_t)c.h2 * (uint32_t)c.w2 + (uint32_t)c.h3 * (uint32_t)c.w3;
+  const int32_t p = (int32_t)acc >> 15;
+  const int32_t r = max(__viaddmin_s32(q, p, 32767), -32768);
+  c.idx2 = __viaddmin_s32_relu(c.idx2, d, kDecIdxScale * AADF_INDEX_MAX);
+  c.w0 += (int32_t)((uint32_t)q * (uint32_t)c.h0 + (1u << 14)) >> 18;
+  c.w1 += (int32_t)((uint32_t)q * (uint32_t)c.h1 + (1u << 14)) >> 18;
+  c.w2 += (int32_t)((uint32_t)q * (uint32_t)c.h2 + (1u << 14)) >> 18;
+  c.w3 += (int32_t)((uint32_t)q * (uint32_t)c.h3 + (1u << 14)) >> 18;
+  c.h3 = c.h2;
+  c.h2 = c.h1;
+  c.h1 = c.h0;
+  c.h0 = r;
+  return r;
+}
+#else
 /* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
 template <int BITS, int POS>
 __device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t, const int *dl)
@@ -94,6 +182,7 @@ __device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const Dec
   c.h0 = r;
   return r;
 }
+#endif
 
 __device__ __forceinline__ uint32_t dec_pack2(int32_t a, int32_t b) { return __byte_perm((uint32_t)a, (uint32_t)b, 0x5410); }
 
@@ -146,214 +235,220 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
   const uint32_t warp = threadIdx.x >> 5;
   unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * G::WARP_BYTES;
   unsigned char *out_rows = in_rows + ((G::IN_BYTES + 15) & ~15);
+#if AAD_DEC_QTAB
+  const int *dl = nullptr;
+#else
   const int *dl = &tab.delta2[0][lane];
+#endif
 
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint32_t warps_per_stream = (nblocks + G::IN_ROWS - 1) / G::IN_ROWS;
-  const uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp;
-  const uint64_t stream = gw / warps_per_stream;
-  if (stream >= p.num_streams) return;                      /* whole warp */
-  const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * G::IN_ROWS;
+  const uint64_t total_warps = (uint64_t)p.num_streams * warps_per_stream;
+  /* persistent: the warps of the grid share out the warp tasks round robin (the tables are built once per CTA) */
+  for (uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp; gw < total_warps; gw += (uint64_t)gridDim.x * kDecWarps) {
+    const uint64_t stream = gw / warps_per_stream;
+    const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * G::IN_ROWS;
 
-  const uint8_t *slot = p.aad + stream * p.aad_stride;
-  const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
-  uint32_t ns = p.uniform_samples;
-  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
-  const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+    const uint8_t *slot = p.aad + stream * p.aad_stride;
+    const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
+    uint32_t ns = p.uniform_samples;
+    if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+    const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
 
-  /* this lane's chain */
-  const uint32_t row = lane / C, ch = lane % C;
-  const uint32_t b = b0 + row;
-  const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
-  const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
-  const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;   /* samples this chain delivers */
-  int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
-  int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;   /* row 0 of the warp */
-  const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb);
+    /* this lane's chain */
+    const uint32_t row = lane / C, ch = lane % C;
+    const uint32_t b = b0 + row;
+    const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+    const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
+    const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;   /* samples this chain delivers */
+    int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+    int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;   /* row 0 of the warp */
+    const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb);
 
-  /* loader role: IN_LOADS 16-byte chunks per lane per window */
-  const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
-  const uint8_t *ld_ptr[G::IN_LOADS];
-  uint32_t ld_smem[G::IN_LOADS];
-#pragma unroll
-  for (int m = 0; m < G::IN_LOADS; m++) {
-    const uint32_t f = lane + 32u * m;
-    const uint32_t rr = f / G::IN_CHUNKS, cc = f % G::IN_CHUNKS;
-    const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
-    ld_ptr[m] = (f < (uint32_t)(G::IN_ROWS * G::IN_CHUNKS)) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
-    ld_smem[m] = rr * G::IN_PITCH + 16u * cc;
-  }
-  const uint8_t *slot_end = slot + size;
-  auto fetch = [&](int m) -> uint4 {
-    const uint8_t *q = ld_ptr[m];
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (q == nullptr || q >= slot_end) return v;
-    if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
-    unsigned char tmp[16];                      /* the chunk that straddles the end of the data: */
-#pragma unroll
-    for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past it read as zero */
-    v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
-    v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
-    v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
-    v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
-    return v;
-  };
-
-  /* reader role: this lane's block row in shared memory */
-  const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
-  const unsigned char *irow = in_rows + row * G::IN_PITCH;
-  unsigned char *orow = out_rows + lane * kDecOutPitch;
-  auto in_u8 = [&](uint32_t pos) -> uint32_t { return irow[a_r + pos]; };
-
-  DecChain c;
-  c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
-
-  const uint32_t windows = (bs + G::TB - 1) / G::TB;
-  uint4 pre[G::IN_LOADS];
-#pragma unroll
-  for (int m = 0; m < G::IN_LOADS; m++) pre[m] = fetch(m);
-
-  uint32_t out_base = 0;                                   /* first output sample of this window */
-  for (uint32_t w = 0; w < windows; w++) {
-    /* stage this window, start the next one */
-#pragma unroll
-    for (int m = 0; m < G::IN_LOADS; m++)
-      if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
-    __syncwarp();
-    if (w + 1 < windows) {
-#pragma unroll
-      for (int m = 0; m < G::IN_LOADS; m++) {
-        if (ld_ptr[m] != nullptr) ld_ptr[m] += G::TB;
-        pre[m] = fetch(m);
-      }
+    /* loader role: IN_LOADS 16-byte chunks per lane per window */
+    const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
+    const uint8_t *ld_ptr[G::IN_LOADS];
+    uint32_t ld_smem[G::IN_LOADS];
+  #pragma unroll
+    for (int m = 0; m < G::IN_LOADS; m++) {
+      const uint32_t f = lane + 32u * m;
+      const uint32_t rr = f / G::IN_CHUNKS, cc = f % G::IN_CHUNKS;
+      const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
+      ld_ptr[m] = (f < (uint32_t)(G::IN_ROWS * G::IN_CHUNKS)) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
+      ld_smem[m] = rr * G::IN_PITCH + 16u * cc;
     }
+    const uint8_t *slot_end = slot + size;
+    auto fetch = [&](int m) -> uint4 {
+      const uint8_t *q = ld_ptr[m];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (q == nullptr || q >= slot_end) return v;
+      if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
+      unsigned char tmp[16];                      /* the chunk that straddles the end of the data: */
+  #pragma unroll
+      for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past it read as zero */
+      v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
+      v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
+      v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
+      v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+      return v;
+    };
 
-    uint32_t produced = 0;      /* samples this chain wrote into its output row in this window */
-    uint32_t pos = 0;           /* byte position inside the window */
-    if (w == 0) {
-      /* block header, src/aad_decoder.c:364-380: u16 (index << 4 | shift), 4 x (u16 weight, u16 history) */
-      const uint32_t hp = AADF_CHANNEL_HEADER_BYTES * ch;
-      const uint32_t head = (in_u8(hp) << 8) | in_u8(hp + 1);
-      c.idx2 = 2 * (int32_t)(int16_t)(head >> 4);
-      c.idx2 = max(0, min(c.idx2, 2 * AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
-      const uint32_t shift = head & 0xFu;
-      int32_t wv[4], hv[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)((in_u8(hp + 2 + 4 * k) << 8) | in_u8(hp + 3 + 4 * k)) << shift);
-        hv[k] = (int32_t)(int16_t)((in_u8(hp + 4 + 4 * k) << 8) | in_u8(hp + 5 + 4 * k));
-      }
-      c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
-      c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
-      const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };   /* src/aad_decoder.c:386-391 */
-      dec_emit<4>(orow, 0, first4);
-      produced = 4;
-      pos = AADF_CHANNEL_HEADER_BYTES * C;
-      if (C == 1) {
-        /* half a step: the 18-byte header leaves the row 2 bytes off word alignment */
-        if (BITS == 3) {
-          int32_t o[16];
-          dec_group3(c, (in_u8(pos) << 16) | (in_u8(pos + 1) << 8) | in_u8(pos + 2), tab, dl, o);
-          dec_group3(c, (in_u8(pos + 3) << 16) | (in_u8(pos + 4) << 8) | in_u8(pos + 5), tab, dl, o + 8);
-          dec_emit<16>(orow, produced, o);
-          produced += 16;
-        } else {
-          const uint32_t v = in_u8(pos) | (in_u8(pos + 1) << 8);
-          int32_t o[2 * (BITS == 4 ? 2 : 4)];
-          dec_byte<BITS, 0>(c, v, tab, dl, o);
-          dec_byte<BITS, 1>(c, v, tab, dl, o + (BITS == 4 ? 2 : 4));
-          dec_emit<2 * (BITS == 4 ? 2 : 4)>(orow, produced, o);
-          produced += 2 * (BITS == 4 ? 2 : 4);
+    /* reader role: this lane's block row in shared memory */
+    const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
+    const unsigned char *irow = in_rows + row * G::IN_PITCH;
+    unsigned char *orow = out_rows + lane * kDecOutPitch;
+    auto in_u8 = [&](uint32_t pos) -> uint32_t { return irow[a_r + pos]; };
+
+    DecChain c;
+    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+
+    const uint32_t windows = (bs + G::TB - 1) / G::TB;
+    uint4 pre[G::IN_LOADS];
+  #pragma unroll
+    for (int m = 0; m < G::IN_LOADS; m++) pre[m] = fetch(m);
+
+    uint32_t out_base = 0;                                   /* first output sample of this window */
+    for (uint32_t w = 0; w < windows; w++) {
+      /* stage this window, start the next one */
+  #pragma unroll
+      for (int m = 0; m < G::IN_LOADS; m++)
+        if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
+      __syncwarp();
+      if (w + 1 < windows) {
+  #pragma unroll
+        for (int m = 0; m < G::IN_LOADS; m++) {
+          if (ld_ptr[m] != nullptr) ld_ptr[m] += G::TB;
+          pre[m] = fetch(m);
         }
-        pos += G::HALF_BYTES;
       }
-    }
 
-    /* whole steps: sliding 32-bit words + funnel shift, any byte alignment */
-    {
-      const uint32_t at = a_r + pos;
-      const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow + (at & ~3u));
-      const uint32_t sh = (at & 3u) * 8u;
-      uint32_t lo = *wp++;
-      const uint32_t steps = (G::TB - pos) / G::STEP_BYTES;
-      for (uint32_t s = 0; s < steps; s++) {
-        if (BITS == 3) {
-          uint32_t x[3];
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
+      uint32_t produced = 0;      /* samples this chain wrote into its output row in this window */
+      uint32_t pos = 0;           /* byte position inside the window */
+      if (w == 0) {
+        /* block header, src/aad_decoder.c:364-380: u16 (index << 4 | shift), 4 x (u16 weight, u16 history) */
+        const uint32_t hp = AADF_CHANNEL_HEADER_BYTES * ch;
+        const uint32_t head = (in_u8(hp) << 8) | in_u8(hp + 1);
+        c.idx2 = kDecIdxScale * (int32_t)(int16_t)(head >> 4);
+        c.idx2 = max(0, min(c.idx2, kDecIdxScale * AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
+        const uint32_t shift = head & 0xFu;
+        int32_t wv[4], hv[4];
+  #pragma unroll
+        for (int k = 0; k < 4; k++) {
+          wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)((in_u8(hp + 2 + 4 * k) << 8) | in_u8(hp + 3 + 4 * k)) << shift);
+          hv[k] = (int32_t)(int16_t)((in_u8(hp + 4 + 4 * k) << 8) | in_u8(hp + 5 + 4 * k));
+        }
+        c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
+        c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
+        const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };   /* src/aad_decoder.c:386-391 */
+        dec_emit<4>(orow, 0, first4);
+        produced = 4;
+        pos = AADF_CHANNEL_HEADER_BYTES * C;
+        if (C == 1) {
+          /* half a step: the 18-byte header leaves the row 2 bytes off word alignment */
+          if (BITS == 3) {
+            int32_t o[16];
+            dec_group3(c, (in_u8(pos) << 16) | (in_u8(pos + 1) << 8) | in_u8(pos + 2), tab, dl, o);
+            dec_group3(c, (in_u8(pos + 3) << 16) | (in_u8(pos + 4) << 8) | in_u8(pos + 5), tab, dl, o + 8);
+            dec_emit<16>(orow, produced, o);
+            produced += 16;
+          } else {
+            const uint32_t v = in_u8(pos) | (in_u8(pos + 1) << 8);
+            int32_t o[2 * (BITS == 4 ? 2 : 4)];
+            dec_byte<BITS, 0>(c, v, tab, dl, o);
+            dec_byte<BITS, 1>(c, v, tab, dl, o + (BITS == 4 ? 2 : 4));
+            dec_emit<2 * (BITS == 4 ? 2 : 4)>(orow, produced, o);
+            produced += 2 * (BITS == 4 ? 2 : 4);
+          }
+          pos += G::HALF_BYTES;
+        }
+      }
+
+      /* whole steps: sliding 32-bit words + funnel shift, any byte alignment */
+      {
+        const uint32_t at = a_r + pos;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow + (at & ~3u));
+        const uint32_t sh = (at & 3u) * 8u;
+        uint32_t lo = *wp++;
+        const uint32_t steps = (G::TB - pos) / G::STEP_BYTES;
+        for (uint32_t s = 0; s < steps; s++) {
+          if (BITS == 3) {
+            uint32_t x[3];
+  #pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const uint32_t hi = *wp++;
+              x[k] = __funnelshift_r(lo, hi, sh);
+              lo = hi;
+            }
+            int32_t o[G::SPS];
+            if (C == 1) {
+              dec_group3(c, __byte_perm(x[0], 0u, 0x4012), tab, dl, o);
+              dec_group3(c, __byte_perm(x[0], x[1], 0x4345), tab, dl, o + 8);
+              dec_group3(c, __byte_perm(x[1], x[2], 0x4234), tab, dl, o + 16);
+              dec_group3(c, __byte_perm(x[2], 0u, 0x4123), tab, dl, o + 24);
+            } else {   /* two channels: groups alternate, 3 bytes each */
+              const uint32_t sel_a = ch ? 0x0345u : 0x0012u, sel_b = ch ? 0x0567u : 0x0234u;
+              dec_group3(c, __byte_perm(x[0], x[1], sel_a), tab, dl, o);
+              dec_group3(c, __byte_perm(x[1], x[2], sel_b), tab, dl, o + 8);
+            }
+            dec_emit<G::SPS>(orow, produced, o);
+          } else {
             const uint32_t hi = *wp++;
-            x[k] = __funnelshift_r(lo, hi, sh);
+            uint32_t v = __funnelshift_r(lo, hi, sh);
             lo = hi;
+            constexpr int PER_BYTE = (BITS == 4) ? 2 : 4;
+            int32_t o[G::SPS];
+            if (C == 1) {
+              dec_byte<BITS, 0>(c, v, tab, dl, o);
+              dec_byte<BITS, 1>(c, v, tab, dl, o + PER_BYTE);
+              dec_byte<BITS, 2>(c, v, tab, dl, o + 2 * PER_BYTE);
+              dec_byte<BITS, 3>(c, v, tab, dl, o + 3 * PER_BYTE);
+            } else {   /* two channels: bytes alternate */
+              v >>= 8u * ch;
+              dec_byte<BITS, 0>(c, v, tab, dl, o);
+              dec_byte<BITS, 2>(c, v, tab, dl, o + PER_BYTE);
+            }
+            dec_emit<G::SPS>(orow, produced, o);
           }
-          int32_t o[G::SPS];
-          if (C == 1) {
-            dec_group3(c, __byte_perm(x[0], 0u, 0x4012), tab, dl, o);
-            dec_group3(c, __byte_perm(x[0], x[1], 0x4345), tab, dl, o + 8);
-            dec_group3(c, __byte_perm(x[1], x[2], 0x4234), tab, dl, o + 16);
-            dec_group3(c, __byte_perm(x[2], 0u, 0x4123), tab, dl, o + 24);
-          } else {   /* two channels: groups alternate, 3 bytes each */
-            const uint32_t sel_a = ch ? 0x0345u : 0x0012u, sel_b = ch ? 0x0567u : 0x0234u;
-            dec_group3(c, __byte_perm(x[0], x[1], sel_a), tab, dl, o);
-            dec_group3(c, __byte_perm(x[1], x[2], sel_b), tab, dl, o + 8);
-          }
-          dec_emit<G::SPS>(orow, produced, o);
-        } else {
-          const uint32_t hi = *wp++;
-          uint32_t v = __funnelshift_r(lo, hi, sh);
-          lo = hi;
-          constexpr int PER_BYTE = (BITS == 4) ? 2 : 4;
-          int32_t o[G::SPS];
-          if (C == 1) {
-            dec_byte<BITS, 0>(c, v, tab, dl, o);
-            dec_byte<BITS, 1>(c, v, tab, dl, o + PER_BYTE);
-            dec_byte<BITS, 2>(c, v, tab, dl, o + 2 * PER_BYTE);
-            dec_byte<BITS, 3>(c, v, tab, dl, o + 3 * PER_BYTE);
-          } else {   /* two channels: bytes alternate */
-            v >>= 8u * ch;
-            dec_byte<BITS, 0>(c, v, tab, dl, o);
-            dec_byte<BITS, 2>(c, v, tab, dl, o + PER_BYTE);
-          }
-          dec_emit<G::SPS>(orow, produced, o);
+          produced += G::SPS;
         }
-        produced += G::SPS;
       }
-    }
-    __syncwarp();
+      __syncwarp();
 
-    /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
-    if (all_full) {
-      /* every chain of the warp delivers a whole block: row addresses are plain arithmetic and the
-       * count is the same for every row -- `produced` (identical in every lane), clipped where the
-       * last window runs past the block; both are multiples of 4 */
-      if (lane * 4u + 4u <= min(produced, spb - out_base)) {
-        const unsigned char *srow = out_rows + 8u * lane;
-        int16_t *dst = grow0 + out_base + 4u * lane;
-#pragma unroll
-        for (uint32_t rr = 0; rr < 32; rr++)
-          *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
-              *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
-      }
-    } else {
-      for (uint32_t rr = 0; rr < 32; rr++) {
-        const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
-        const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
-        const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
-        if (n_rr <= out_base) continue;                       /* uniform */
-        const uint32_t count = min(made, n_rr - out_base);
-        int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
-        const unsigned char *srow = out_rows + rr * kDecOutPitch;
-        const uint32_t s0 = lane * 4u;
-        if (s0 + 4u <= count) {
-          *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
-        } else {
-          for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+      /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
+      if (all_full) {
+        /* every chain of the warp delivers a whole block: row addresses are plain arithmetic and the
+         * count is the same for every row -- `produced` (identical in every lane), clipped where the
+         * last window runs past the block; both are multiples of 4 */
+        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst = grow0 + out_base + 4u * lane;
+  #pragma unroll
+          for (uint32_t rr = 0; rr < 32; rr++)
+            *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
+                *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+        }
+      } else {
+        for (uint32_t rr = 0; rr < 32; rr++) {
+          const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+          const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+          const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+          if (n_rr <= out_base) continue;                       /* uniform */
+          const uint32_t count = min(made, n_rr - out_base);
+          int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+          const unsigned char *srow = out_rows + rr * kDecOutPitch;
+          const uint32_t s0 = lane * 4u;
+          if (s0 + 4u <= count) {
+            *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+          } else {
+            for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+          }
         }
       }
+      out_base += produced;       /* identical in every lane */
+      __syncwarp();
     }
-    out_base += produced;       /* identical in every lane */
-    __syncwarp();
   }
 }
 
@@ -372,7 +467,6 @@ template <int BITS>
 __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_decode_params p)
 {
   constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
-  constexpr uint32_t GS = (BITS == 4) ? 2 : (BITS == 3 ? 8 : 4);
   constexpr int kLoads = BITS + 1;          /* ceil(rows * chunks / 32) <= BITS + 1 for every C */
   extern __shared__ __align__(16) unsigned char dec_smem[];
   DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
@@ -389,186 +483,192 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
   const uint32_t warp = threadIdx.x >> 5;
   unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * (in_bytes + 32u * kDecOutPitch);
   unsigned char *out_rows = in_rows + in_bytes;
+#if AAD_DEC_QTAB
+  const int *dl = nullptr;
+#else
   const int *dl = &tab.delta2[0][lane];
+#endif
 
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint32_t warps_per_stream = (nblocks + rows - 1) / rows;
-  const uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp;
-  const uint64_t stream = gw / warps_per_stream;
-  if (stream >= p.num_streams) return;                      /* whole warp */
-  const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * rows;
+  const uint64_t total_warps = (uint64_t)p.num_streams * warps_per_stream;
+  /* persistent: the warps of the grid share out the warp tasks round robin (the tables are built once per CTA) */
+  for (uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp; gw < total_warps; gw += (uint64_t)gridDim.x * kDecWarps) {
+    const uint64_t stream = gw / warps_per_stream;
+    const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * rows;
 
-  const uint8_t *slot = p.aad + stream * p.aad_stride;
-  const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
-  uint32_t ns = p.uniform_samples;
-  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
-  const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+    const uint8_t *slot = p.aad + stream * p.aad_stride;
+    const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
+    uint32_t ns = p.uniform_samples;
+    if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+    const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
 
-  /* this lane's chain (idle lanes shadow row 0 and deliver nothing) */
-  const bool lane_on = lane < active;
-  const uint32_t row = lane_on ? lane / C : 0u, ch = lane_on ? lane % C : 0u;
-  const uint32_t b = b0 + row;
-  const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
-  const bool have = lane_on && b < p.block_end && (uint64_t)b * spb < ns &&
-                    blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
-  const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;
-  int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
-  int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;
-  const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb || !lane_on);
+    /* this lane's chain (idle lanes shadow row 0 and deliver nothing) */
+    const bool lane_on = lane < active;
+    const uint32_t row = lane_on ? lane / C : 0u, ch = lane_on ? lane % C : 0u;
+    const uint32_t b = b0 + row;
+    const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+    const bool have = lane_on && b < p.block_end && (uint64_t)b * spb < ns &&
+                      blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
+    const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;
+    int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+    int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;
+    const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb || !lane_on);
 
-  /* loader role */
-  const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
-  const uint8_t *ld_ptr[kLoads];
-  uint32_t ld_smem[kLoads];
-#pragma unroll
-  for (int m = 0; m < kLoads; m++) {
-    const uint32_t f = lane + 32u * m;
-    const uint32_t rr = f / chunks, cc = f % chunks;
-    const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
-    ld_ptr[m] = (f < rows * chunks) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
-    ld_smem[m] = rr * pitch + 16u * cc;
-  }
-  const uint8_t *slot_end = slot + size;
-  auto fetch = [&](int m) -> uint4 {
-    const uint8_t *q = ld_ptr[m];
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (q == nullptr || q >= slot_end) return v;
-    if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
-    unsigned char tmp[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past the data read as zero */
-    v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
-    v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
-    v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
-    v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
-    return v;
-  };
-
-  /* reader role */
-  const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
-  const unsigned char *irow = in_rows + row * pitch + a_r;
-  unsigned char *orow = out_rows + lane * kDecOutPitch;
-
-  DecChain c;
-  c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
-
-  const uint32_t windows = (bs + TB - 1) / TB;
-  const uint32_t gstride = GB * C;
-  uint4 pre[kLoads];
-#pragma unroll
-  for (int m = 0; m < kLoads; m++) pre[m] = fetch(m);
-
-  uint32_t out_base = 0;
-  for (uint32_t w = 0; w < windows; w++) {
-#pragma unroll
-    for (int m = 0; m < kLoads; m++)
-      if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
-    __syncwarp();
-    if (w + 1 < windows) {
-#pragma unroll
-      for (int m = 0; m < kLoads; m++) {
-        if (ld_ptr[m] != nullptr) ld_ptr[m] += TB;
-        pre[m] = fetch(m);
-      }
+    /* loader role */
+    const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
+    const uint8_t *ld_ptr[kLoads];
+    uint32_t ld_smem[kLoads];
+  #pragma unroll
+    for (int m = 0; m < kLoads; m++) {
+      const uint32_t f = lane + 32u * m;
+      const uint32_t rr = f / chunks, cc = f % chunks;
+      const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
+      ld_ptr[m] = (f < rows * chunks) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
+      ld_smem[m] = rr * pitch + 16u * cc;
     }
+    const uint8_t *slot_end = slot + size;
+    auto fetch = [&](int m) -> uint4 {
+      const uint8_t *q = ld_ptr[m];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (q == nullptr || q >= slot_end) return v;
+      if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
+      unsigned char tmp[16];
+  #pragma unroll
+      for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past the data read as zero */
+      v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
+      v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
+      v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
+      v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+      return v;
+    };
 
-    uint32_t produced = 0;
-    uint32_t pos = 0;
-    if (w == 0) {   /* block header, src/aad_decoder.c:364-391 */
-      const unsigned char *hp = irow + AADF_CHANNEL_HEADER_BYTES * ch;
-      const uint32_t head = ((uint32_t)hp[0] << 8) | hp[1];
-      c.idx2 = 2 * (int32_t)(int16_t)(head >> 4);
-      c.idx2 = max(0, min(c.idx2, 2 * AADF_INDEX_MAX));
-      const uint32_t shift = head & 0xFu;
-      int32_t wv[4], hv[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)(((uint32_t)hp[2 + 4 * k] << 8) | hp[3 + 4 * k]) << shift);
-        hv[k] = (int32_t)(int16_t)(((uint32_t)hp[4 + 4 * k] << 8) | hp[5 + 4 * k]);
-      }
-      c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
-      c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
-      const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };
-      dec_emit<4>(orow, 0, first4);
-      produced = 4;
-      pos = AADF_CHANNEL_HEADER_BYTES * C;
-    }
+    /* reader role */
+    const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
+    const unsigned char *irow = in_rows + row * pitch + a_r;
+    unsigned char *orow = out_rows + lane * kDecOutPitch;
 
-    /* this chain's groups of the window: GB bytes every GB * C bytes; 4 (2-bit, 4-bit) or 8 (3-bit)
-     * samples per turn so the shared output row takes whole 8-byte pieces */
-    {
-      const unsigned char *bp = irow + pos + GB * ch;
-      const uint32_t groups = (TB - pos) / gstride;          /* even for 4-bit in every window */
-      if (BITS == 4) {
-#pragma unroll 2
-        for (uint32_t g = 0; g < groups; g += 2) {
-          const uint32_t v = (uint32_t)bp[0] | ((uint32_t)bp[gstride] << 8);
-          bp += 2u * gstride;
-          int32_t o[4];
-          dec_byte<4, 0>(c, v, tab, dl, o);
-          dec_byte<4, 1>(c, v, tab, dl, o + 2);
-          dec_emit<4>(orow, produced, o);
-          produced += 4;
+    DecChain c;
+    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+
+    const uint32_t windows = (bs + TB - 1) / TB;
+    const uint32_t gstride = GB * C;
+    uint4 pre[kLoads];
+  #pragma unroll
+    for (int m = 0; m < kLoads; m++) pre[m] = fetch(m);
+
+    uint32_t out_base = 0;
+    for (uint32_t w = 0; w < windows; w++) {
+  #pragma unroll
+      for (int m = 0; m < kLoads; m++)
+        if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
+      __syncwarp();
+      if (w + 1 < windows) {
+  #pragma unroll
+        for (int m = 0; m < kLoads; m++) {
+          if (ld_ptr[m] != nullptr) ld_ptr[m] += TB;
+          pre[m] = fetch(m);
         }
-      } else if (BITS == 3) {
-#pragma unroll 2
-        for (uint32_t g = 0; g < groups; g++) {
-          const uint32_t v = ((uint32_t)bp[0] << 16) | ((uint32_t)bp[1] << 8) | bp[2];
-          bp += gstride;
-          int32_t o[8];
-          dec_group3(c, v, tab, dl, o);
-          dec_emit<8>(orow, produced, o);
-          produced += 8;
+      }
+
+      uint32_t produced = 0;
+      uint32_t pos = 0;
+      if (w == 0) {   /* block header, src/aad_decoder.c:364-391 */
+        const unsigned char *hp = irow + AADF_CHANNEL_HEADER_BYTES * ch;
+        const uint32_t head = ((uint32_t)hp[0] << 8) | hp[1];
+        c.idx2 = kDecIdxScale * (int32_t)(int16_t)(head >> 4);
+        c.idx2 = max(0, min(c.idx2, kDecIdxScale * AADF_INDEX_MAX));
+        const uint32_t shift = head & 0xFu;
+        int32_t wv[4], hv[4];
+  #pragma unroll
+        for (int k = 0; k < 4; k++) {
+          wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)(((uint32_t)hp[2 + 4 * k] << 8) | hp[3 + 4 * k]) << shift);
+          hv[k] = (int32_t)(int16_t)(((uint32_t)hp[4 + 4 * k] << 8) | hp[5 + 4 * k]);
+        }
+        c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
+        c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
+        const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };
+        dec_emit<4>(orow, 0, first4);
+        produced = 4;
+        pos = AADF_CHANNEL_HEADER_BYTES * C;
+      }
+
+      /* this chain's groups of the window: GB bytes every GB * C bytes; 4 (2-bit, 4-bit) or 8 (3-bit)
+       * samples per turn so the shared output row takes whole 8-byte pieces */
+      {
+        const unsigned char *bp = irow + pos + GB * ch;
+        const uint32_t groups = (TB - pos) / gstride;          /* even for 4-bit in every window */
+        if (BITS == 4) {
+  #pragma unroll 2
+          for (uint32_t g = 0; g < groups; g += 2) {
+            const uint32_t v = (uint32_t)bp[0] | ((uint32_t)bp[gstride] << 8);
+            bp += 2u * gstride;
+            int32_t o[4];
+            dec_byte<4, 0>(c, v, tab, dl, o);
+            dec_byte<4, 1>(c, v, tab, dl, o + 2);
+            dec_emit<4>(orow, produced, o);
+            produced += 4;
+          }
+        } else if (BITS == 3) {
+  #pragma unroll 2
+          for (uint32_t g = 0; g < groups; g++) {
+            const uint32_t v = ((uint32_t)bp[0] << 16) | ((uint32_t)bp[1] << 8) | bp[2];
+            bp += gstride;
+            int32_t o[8];
+            dec_group3(c, v, tab, dl, o);
+            dec_emit<8>(orow, produced, o);
+            produced += 8;
+          }
+        } else {
+  #pragma unroll 2
+          for (uint32_t g = 0; g < groups; g++) {
+            const uint32_t v = bp[0];
+            bp += gstride;
+            int32_t o[4];
+            dec_byte<2, 0>(c, v, tab, dl, o);
+            dec_emit<4>(orow, produced, o);
+            produced += 4;
+          }
+        }
+      }
+      __syncwarp();
+
+      /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
+      if (all_full) {
+        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst_blk = grow0 + out_base + 4u * lane;
+          int16_t *dst = dst_blk;
+          uint32_t rch = 0;
+  #pragma unroll 4
+          for (uint32_t rr = 0; rr < active; rr++) {
+            *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+            dst += p.pcm_ch_stride;
+            if (++rch == C) { rch = 0; dst_blk += spb; dst = dst_blk; }
+          }
         }
       } else {
-#pragma unroll 2
-        for (uint32_t g = 0; g < groups; g++) {
-          const uint32_t v = bp[0];
-          bp += gstride;
-          int32_t o[4];
-          dec_byte<2, 0>(c, v, tab, dl, o);
-          dec_emit<4>(orow, produced, o);
-          produced += 4;
-        }
-      }
-    }
-    __syncwarp();
-
-    /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
-    if (all_full) {
-      if (lane * 4u + 4u <= min(produced, spb - out_base)) {
-        const unsigned char *srow = out_rows + 8u * lane;
-        int16_t *dst_blk = grow0 + out_base + 4u * lane;
-        int16_t *dst = dst_blk;
-        uint32_t rch = 0;
-#pragma unroll 4
         for (uint32_t rr = 0; rr < active; rr++) {
-          *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
-          dst += p.pcm_ch_stride;
-          if (++rch == C) { rch = 0; dst_blk += spb; dst = dst_blk; }
+          const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+          const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+          const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+          if (n_rr <= out_base) continue;                       /* uniform */
+          const uint32_t count = min(made, n_rr - out_base);
+          int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+          const unsigned char *srow = out_rows + rr * kDecOutPitch;
+          const uint32_t s0 = lane * 4u;
+          if (s0 + 4u <= count) {
+            *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+          } else {
+            for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+          }
         }
       }
-    } else {
-      for (uint32_t rr = 0; rr < active; rr++) {
-        const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
-        const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
-        const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
-        if (n_rr <= out_base) continue;                       /* uniform */
-        const uint32_t count = min(made, n_rr - out_base);
-        int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
-        const unsigned char *srow = out_rows + rr * kDecOutPitch;
-        const uint32_t s0 = lane * 4u;
-        if (s0 + 4u <= count) {
-          *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
-        } else {
-          for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
-        }
-      }
+      out_base += produced;       /* identical in every lane */
+      __syncwarp();
     }
-    out_base += produced;       /* identical in every lane */
-    __syncwarp();
   }
 }
 
@@ -585,6 +685,25 @@ inline bool dec_fast_eligible(const aadk_decode_params &p)
   return true;
 }
 
+#ifndef AAD_DEC_PERSIST
+#define AAD_DEC_PERSIST 1
+#endif
+/* One wave of CTAs (SMs x resident CTAs per SM), each warp looping over its share of the warp tasks,
+ * so the shared-memory tables are built once per resident CTA instead of once per 4 tasks. */
+template <typename K>
+int dec_persistent_grid(K kernel, size_t smem, uint64_t warps, unsigned *grid)
+{
+  const uint64_t ctas = (warps + kDecWarps - 1) / kDecWarps;
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDecWarps * 32, smem)) != cudaSuccess) return (int)e;
+  const uint64_t wave = (uint64_t)sms * (uint64_t)(per_sm > 0 ? per_sm : 1);
+  *grid = (unsigned)((AAD_DEC_PERSIST && ctas > wave) ? wave : ctas);
+  return 0;
+}
+
 template <int BITS, int C>
 int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
 {
@@ -595,7 +714,8 @@ int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
   if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
-  const unsigned grid = (unsigned)((warps + kDecWarps - 1) / kDecWarps);
+  unsigned grid = 0;
+  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C>, smem, warps, &grid)) return rc;
   aad_decode_fast<BITS, C><<<grid, kDecWarps * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
@@ -610,7 +730,8 @@ int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
   if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + rows - 1) / rows);
-  const unsigned grid = (unsigned)((warps + kDecWarps - 1) / kDecWarps);
+  unsigned grid = 0;
+  if (int rc = dec_persistent_grid(aad_decode_wide<BITS>, smem, warps, &grid)) return rc;
   aad_decode_wide<BITS><<<grid, kDecWarps * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
