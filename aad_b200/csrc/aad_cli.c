@@ -29,7 +29,7 @@ enum { MODE_ENCODE, MODE_DECODE, MODE_RECONSTRUCT, MODE_GAP, MODE_CALCULATE, MOD
 struct options {
   int mode_set[NUM_MODES];
   int help, version, ms;
-  const char *bits, *block, *trials, *device, *batch;
+  const char *bits, *block, *trials, *device, *batch, *segment;
   const char *files[2];
   int num_files;
 };
@@ -54,6 +54,7 @@ static const struct option_spec k_specs[] = {
   { 'm', "ms-conversion", 0, "Switch to use LR to MS conversion (default: no)" },
   { 'D', "device", 1, "CUDA device(s): index, comma separated list, or \"all\" (default: 0); with several, -d shards one file by block range and --batch shards files" },
   { 'B', "batch", 1, "With -e / -d: file listing one \"INPUT OUTPUT\" pair per line, processed as batches" },
+  { 'S', "segment-blocks", 1, "Encode every run of N blocks as an independent chain (parallel encode of one long file; decodes with any AAD decoder but is NOT byte-identical to the reference encoder's output) (default: 0 = off)" },
   { 'h', "help", 0, "Show help message" },
   { 'v', "version", 0, "Show version information" },
 };
@@ -74,6 +75,7 @@ static void apply_option(struct options *o, char short_name, const char *value)
     case 'm': o->ms = 1; break;
     case 'D': o->device = value; break;
     case 'B': o->batch = value; break;
+    case 'S': o->segment = value; break;
     case 'h': o->help = 1; break;
     case 'v': o->version = 1; break;
     default: break;
@@ -712,6 +714,11 @@ int main(int argc, char **argv)
     return 1;
   }
   g_have_gpu = 1;
+  if (o.segment) {   /* extension: segment-parallel encoding on every device this run uses */
+    const uint32_t seg = (uint32_t)strtoul(o.segment, NULL, 10);
+    for (int d = 0; d < (g_group ? AADGpuGroup_Size(g_group) : 1); d++)
+      AADGpu_SetEncodeSegmentBlocks(g_group ? AADGpuGroup_Device(g_group, d) : gpu, seg);
+  }
   int rc;
   if (batch) rc = (mode == MODE_ENCODE) ? execute_encode_batch(gpu, o.batch, &cli) : execute_decode_batch(gpu, o.batch);
   else if (mode == MODE_ENCODE) rc = execute_encode(gpu, o.files[0], o.files[1], &cli);

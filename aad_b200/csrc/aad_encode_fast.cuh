@@ -534,14 +534,17 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
 
+  /* chain = (stream, segment, channel); one segment spanning the stream unless segment mode is on */
+  const uint32_t segs = p.segment_blocks ? p.num_segments : 1u;
   const uint64_t chain = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stream = chain / C;
+  const uint64_t stream = chain / ((uint64_t)C * segs);
   if (stream >= p.num_streams) return;
+  const uint32_t seg = (uint32_t)(chain / C % segs);
   const uint32_t ch = (uint32_t)(chain % C);
   const uint32_t ns = p.num_samples ? p.num_samples[stream] : p.uniform_samples;
 
   uint8_t *out = p.aad + stream * p.aad_stride;
-  if (ch == 0 && p.block_begin == 0) {
+  if (ch == 0 && seg == 0 && p.block_begin == 0) {
     if (ns > 0) aadf_write_file_header(out, C, ns, p.sampling_rate, BITS, bs, spb, p.geo.ms);
     if (p.out_sizes) p.out_sizes[stream] = ns ? (uint32_t)aadf_stream_bytes(ns, C, BITS, bs, spb) : 0u;
   }
@@ -564,14 +567,19 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   S.idx8 = kEncIdxScale * (p.state_in ? p.state_in[st + 4] : 0);
 
   const uint32_t trials = p.trials;
-  const uint32_t nblk = min(aadf_num_blocks(ns, spb), p.block_end);
+  /* this chain's blocks: [seg_first, seg_end) cut to the launch's block range */
+  const uint32_t seg_first = p.segment_blocks ? seg * p.segment_blocks : 0u;
+  const uint32_t seg_end = p.segment_blocks ? seg_first + p.segment_blocks : 0xFFFFFFFFu;
+  const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), p.block_end), seg_end);
+  const uint32_t b_begin = max(p.block_begin, seg_first);
+  if (p.segment_blocks && b_begin == seg_first) S.w0 = S.w1 = S.w2 = S.w3 = S.idx8 = 0;   /* a segment starts like a new stream */
 
   EncJob<MS> job, job2;
   job.ring.base = (uint32_t)__cvta_generic_to_shared(enc_smem) + kEncLutBytes +
                   (threadIdx.x >> 5) * ((PAIR ? 2u : 1u) * EncRing<MS>::kWarpBytes) + (threadIdx.x & 31u) * 16u;
   job2.ring.base = job.ring.base + EncRing<MS>::kWarpBytes;
 
-  for (uint32_t b = p.block_begin; b < nblk; b++) {
+  for (uint32_t b = b_begin; b < nblk; b++) {
     const uint32_t first = b * spb;
     const uint32_t n = min(spb, ns - first);
     /* src/aad_encoder.c:470-562 then :565-727, as one loop over passes (a single copy of the
@@ -584,7 +592,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
     double best_rmse = 0.0;
     const uint32_t dry = trials ? 1u + 2u * trials : 0u;
     uint32_t k = 0;
-    if (PAIR && dry && b > 0) {   /* passes 0 and 1 both start from the carried state: run them together */
+    if (PAIR && dry && b > seg_first) {   /* passes 0 and 1 both start from the carried state: run them together */
       job.c.set(S);  job.first = first;        job.n = n;    job.run = true;  job.emit = false;
       job2.c.set(S); job2.first = first - spb; job2.n = spb; job2.run = true; job2.emit = false;
       job.blk = job2.blk = out;
@@ -596,7 +604,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
     for (; k <= dry; k++) {
       const bool emit = (k == dry);
       const bool on_prev = !emit && (k & 1u) != 0u;
-      if (on_prev && b == 0) continue;
+      if (on_prev && b == seg_first) continue;
       if (!emit && !on_prev && k > 0) cand = run;
       job.c.set(emit ? best : run);
       job.first = on_prev ? first - spb : first;
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
     }
   }
 
-  if (p.state_out) {
+  if (p.state_out && (!p.segment_blocks || b_begin < nblk)) {
     p.state_out[st + 0] = S.w0;
     p.state_out[st + 1] = S.w1;
     p.state_out[st + 2] = S.w2;
@@ -641,7 +649,7 @@ inline bool enc_fast_eligible(const aadk_encode_params &p)
 template <int BITS, int MS, int PAIR>
 int enc_fast_launch_as(const aadk_encode_params &p, cudaStream_t s)
 {
-  const uint64_t lanes = (uint64_t)p.num_streams * p.geo.channels;
+  const uint64_t lanes = (uint64_t)p.num_streams * p.geo.channels * (p.segment_blocks ? p.num_segments : 1u);
   const size_t ring_bytes = (size_t)(PAIR ? 2 : 1) * EncRing<MS>::kWarpBytes;
   /* per device, so set on every launch (cheap) */
   cudaError_t e = cudaFuncSetAttribute(aad_encode_fast<BITS, MS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -675,7 +683,7 @@ template <int BITS>
 int enc_fast_launch(const aadk_encode_params &p, cudaStream_t s)
 {
   /* up to one warp per scheduler (148 SMs x 4): pair the independent dry passes inside each thread */
-  const uint64_t chains = (uint64_t)p.num_streams * p.geo.channels;
+  const uint64_t chains = (uint64_t)p.num_streams * p.geo.channels * (p.segment_blocks ? p.num_segments : 1u);
   const bool pair = p.trials >= 1 && chains <= 148ull * 4 * 32 && g_enc_pairing != 0;
   const bool ms = p.geo.ms && p.geo.channels >= 2;
   if (pair) return ms ? enc_fast_launch_as<BITS, 1, 1>(p, s) : enc_fast_launch_as<BITS, 0, 1>(p, s);

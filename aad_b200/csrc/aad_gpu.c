@@ -189,6 +189,26 @@ int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes)
 
 /* The checks AADEncoder_SetEncodeParameter (src/aad_encoder.c:741-770) and
  * AADEncoder_EncodeHeader (src/aad_encoder.c:149-185) apply, in that order. */
+/* ---- segment mode ---------------------------------------------------------------------------- */
+
+AADApiResult AADGpu_SetEncodeSegmentBlocks(struct AADGpu *gpu, uint32_t blocks)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  gpu->segment_blocks = blocks;
+  return AAD_APIRESULT_OK;
+}
+
+uint32_t AADGpu_GetEncodeSegmentBlocks(const struct AADGpu *gpu) { return gpu ? gpu->segment_blocks : 0; }
+
+/* chains per (stream, channel) for a stream of total_blocks blocks; fills the kernel parameters */
+static uint32_t apply_segments(const struct AADGpu *gpu, struct aadk_encode_params *p, uint32_t total_blocks)
+{
+  p->segment_blocks = gpu->segment_blocks;
+  p->num_segments = gpu->segment_blocks ? (total_blocks + gpu->segment_blocks - 1) / gpu->segment_blocks : 1;
+  if (p->num_segments == 0) p->num_segments = 1;
+  return p->num_segments;
+}
+
 static AADApiResult check_encode_shape(const struct AADEncodeParameter *prm, uint32_t num_samples,
                                        struct aadf_geometry *geo)
 {
@@ -265,6 +285,7 @@ AADApiResult AADGpu_EncodeBatchDevice(struct AADGpu *gpu, const struct AADGpuBat
   p.out_sizes = out_sizes_dev;
   p.block_begin = 0;
   p.block_end = aadf_num_blocks(batch->num_samples, geo.samples_per_block);
+  (void)apply_segments(gpu, &p, p.block_end);
   CU((cudaError_t)aadk_launch_encode(&p, stream), "encode kernel launch");
   return AAD_APIRESULT_OK;
 }
@@ -357,6 +378,7 @@ AADApiResult AADGpu_Interleave16Device(struct AADGpu *gpu, const int16_t *planar
 
 static uint64_t round_up64(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
+
 /* how many block-range slices to cut the copies into: ~32 MiB of PCM each, at most AADGPU_MAX_SLICES */
 static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
 {
@@ -418,12 +440,14 @@ AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
   const uint64_t astride = round_up64(aadf_stream_bytes_bound(ns, bs, spb) + 1, 128);
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)N * astride + 128)) return AAD_APIRESULT_NG;
-  if (!aadgpu_reserve(gpu, &gpu->state, (size_t)N * C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
+  const uint32_t segs = gpu->segment_blocks ? (nblk + gpu->segment_blocks - 1) / gpu->segment_blocks : 1;
+  const size_t state_bytes = (size_t)N * C * (segs ? segs : 1) * AADK_STATE_WORDS * 4;
+  if (!aadgpu_reserve(gpu, &gpu->state, state_bytes)) return AAD_APIRESULT_NG;
   if (num_samples && !aadgpu_reserve(gpu, &gpu->lens, (size_t)N * 4)) return AAD_APIRESULT_NG;
   int16_t *d_pcm = (int16_t *)gpu->pcm.ptr;
   uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;   /* block 0 of every stream lands 32-byte aligned */
 
-  CU(cudaMemsetAsync(gpu->state.ptr, 0, (size_t)N * C * AADK_STATE_WORDS * 4, gpu->s_run), "memset state");
+  CU(cudaMemsetAsync(gpu->state.ptr, 0, state_bytes, gpu->s_run), "memset state");
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)N * astride + 128, gpu->s_run), "memset aad");
   if (num_samples)
     CU(cudaMemcpyAsync(gpu->lens.ptr, num_samples, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D lengths");
@@ -443,6 +467,7 @@ AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
   p.aad_stride = astride;
   p.state_in = (const int32_t *)gpu->state.ptr;
   p.state_out = (int32_t *)gpu->state.ptr;
+  (void)apply_segments(gpu, &p, nblk);
 
   const uint32_t slices = pick_slices((uint64_t)N * C * ns * 2, nblk);
   for (uint32_t k = 0; k < slices; k++) {
@@ -567,13 +592,15 @@ AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatc
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->pcm2, (size_t)N * C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)N * astride + 128)) return AAD_APIRESULT_NG;
-  if (!aadgpu_reserve(gpu, &gpu->state, (size_t)N * C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
+  const uint32_t segs = gpu->segment_blocks ? (nblk + gpu->segment_blocks - 1) / gpu->segment_blocks : 1;
+  const size_t state_bytes = (size_t)N * C * (segs ? segs : 1) * AADK_STATE_WORDS * 4;
+  if (!aadgpu_reserve(gpu, &gpu->state, state_bytes)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->lens, (size_t)N * 4)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->sizes, (size_t)N * 4)) return AAD_APIRESULT_NG;
   int16_t *d_pcm = (int16_t *)gpu->pcm.ptr, *d_out = (int16_t *)gpu->pcm2.ptr;
   uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
 
-  CU(cudaMemsetAsync(gpu->state.ptr, 0, (size_t)N * C * AADK_STATE_WORDS * 4, gpu->s_run), "memset state");
+  CU(cudaMemsetAsync(gpu->state.ptr, 0, state_bytes, gpu->s_run), "memset state");
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)N * astride + 128, gpu->s_run), "memset aad");
   if (num_samples)
     CU(cudaMemcpyAsync(gpu->lens.ptr, num_samples, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D lengths");
@@ -594,6 +621,7 @@ AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatc
   e.out_sizes = (uint32_t *)gpu->sizes.ptr;          /* written with the first slice: the decoder's byte bounds */
   e.state_in = (const int32_t *)gpu->state.ptr;
   e.state_out = (int32_t *)gpu->state.ptr;
+  (void)apply_segments(gpu, &e, nblk);
 
   struct aadk_decode_params d;
   memset(&d, 0, sizeof(d));
@@ -776,6 +804,7 @@ static AADApiResult encode_interleaved_device(struct AADGpu *gpu, const struct A
   p.aad_stride = bound;
   p.block_begin = 0;
   p.block_end = aadf_num_blocks(num_samples, geo->samples_per_block);
+  (void)apply_segments(gpu, &p, p.block_end);
   CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
   *pitch_out = pitch;
   *bytes_out = bytes;

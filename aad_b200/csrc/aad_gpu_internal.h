@@ -27,6 +27,7 @@ struct AADGpu {
   cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES];
   struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2;
   int lut_ready;
+  uint32_t segment_blocks;   /* AADGpu_SetEncodeSegmentBlocks; 0 = the reference's whole-stream state carry */
 };
 
 /* error plumbing: records a message for AADGpu_LastError() and returns AAD_APIRESULT_NG */

@@ -276,14 +276,16 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
 
+  const uint32_t segs = p.segment_blocks ? p.num_segments : 1u;   /* segment mode: aad_kernels.h */
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stream = t / C;
+  const uint64_t stream = t / ((uint64_t)C * segs);
   if (stream >= p.num_streams) return;
+  const uint32_t seg = (uint32_t)(t / C % segs);
   const uint32_t ch = (uint32_t)(t % C);
   const uint32_t ns = p.num_samples ? p.num_samples[stream] : p.uniform_samples;
 
   uint8_t *out = p.aad + stream * p.aad_stride;
-  if (ch == 0 && p.block_begin == 0) {
+  if (ch == 0 && seg == 0 && p.block_begin == 0) {
     if (ns > 0) aadf_write_file_header(out, C, ns, p.sampling_rate, BITS, bs, spb, p.geo.ms);
     if (p.out_sizes) p.out_sizes[stream] = ns ? (uint32_t)aadf_stream_bytes(ns, C, BITS, bs, spb) : 0u;
   }
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
   }
 
   Chain c;
-  const uint64_t st = (stream * C + ch) * AADK_STATE_WORDS;
+  const uint64_t st = t * AADK_STATE_WORDS;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     c.h[k] = 0;
@@ -308,8 +310,16 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
   }
   c.idx = p.state_in ? p.state_in[st + 4] : 0;
 
-  const uint32_t nblk = min(aadf_num_blocks(ns, spb), p.block_end);
-  for (uint32_t b = p.block_begin; b < nblk; b++) {
+  const uint32_t seg_first = p.segment_blocks ? seg * p.segment_blocks : 0u;
+  const uint32_t seg_end = p.segment_blocks ? seg_first + p.segment_blocks : 0xFFFFFFFFu;
+  const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), p.block_end), seg_end);
+  const uint32_t b_begin = max(p.block_begin, seg_first);
+  if (p.segment_blocks && b_begin == seg_first) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) c.w[k] = 0;
+    c.idx = 0;
+  }
+  for (uint32_t b = b_begin; b < nblk; b++) {
     const uint32_t first = b * spb;
     const uint32_t n = min(spb, ns - first);
     const uint32_t limit = first + n;
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
       Chain probe = c, best = c, run = c;
       double best_rmse = trial_rmse<BITS>(probe, src, first, n, tab);
       for (uint32_t tr = 0; tr < p.trials; tr++) {
-        if (b > 0) (void)trial_rmse<BITS>(run, src, first - spb, spb, tab);
+        if (b > seg_first) (void)trial_rmse<BITS>(run, src, first - spb, spb, tab);
         const Chain cand = run;
         const double rmse = trial_rmse<BITS>(run, src, first, n, tab);
         if (best_rmse > rmse) { best_rmse = rmse; best = cand; }
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
     }
   }
 
-  if (p.state_out) {
+  if (p.state_out && (!p.segment_blocks || b_begin < nblk)) {
 #pragma unroll
     for (int k = 0; k < 4; k++) p.state_out[st + k] = c.w[k];
     p.state_out[st + 4] = c.idx;
@@ -488,7 +498,8 @@ int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
 int aadk_launch_encode(const struct aadk_encode_params *p, void *stream)
 {
   cudaStream_t s = (cudaStream_t)stream;
-  const uint64_t threads = (uint64_t)p->num_streams * p->geo.channels;
+  if (p->segment_blocks && p->num_segments == 0) return (int)cudaErrorInvalidValue;
+  const uint64_t threads = (uint64_t)p->num_streams * p->geo.channels * (p->segment_blocks ? p->num_segments : 1u);
   if (threads == 0 || p->block_end <= p->block_begin) return 0;
   if (enc_fast_eligible(*p) && !g_force_generic) {
     int rc;

@@ -52,6 +52,14 @@ struct aadk_encode_params {
   int32_t *state_out;          /* same shape, nullable */
   uint32_t block_begin;        /* blocks [block_begin, block_end) of every stream are encoded; the */
   uint32_t block_end;          /* chain state enters through state_in and leaves through state_out */
+  /* Segment mode (NOT byte-identical to the reference encoder, which carries its state through the whole
+   * stream; off when segment_blocks == 0): every run of segment_blocks blocks is encoded as a stream of
+   * its own -- zero weights and step index at its first block, no previous-block trial pass there -- so a
+   * stream is num_segments independent chains per channel.  The state arrays are then
+   * [stream][segment][channel][AADK_STATE_WORDS]; num_segments must be the same for every launch that
+   * shares them. */
+  uint32_t segment_blocks;
+  uint32_t num_segments;       /* >= 1 when segment_blocks != 0 */
 };
 
 int aadk_launch_decode(const struct aadk_decode_params *p, void *stream);

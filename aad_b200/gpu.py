@@ -34,6 +34,7 @@ class GpuApi:
         "AADGpu_StreamBytesBound", "AADGpu_StreamBytes", "AADGpu_EncodeBatchDevice", "AADGpu_DecodeBatchDevice",
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_ReconstructBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
         "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath", "AADGpu_SetEncoderPairing",
+        "AADGpu_SetEncodeSegmentBlocks", "AADGpu_GetEncodeSegmentBlocks",
         "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16",
         "AADGpuGroup_Create", "AADGpuGroup_Destroy", "AADGpuGroup_Size", "AADGpuGroup_Device",
         "AADGpuGroup_EncodeBatch", "AADGpuGroup_DecodeBatch", "AADGpuGroup_DecodeInterleaved16",
@@ -67,6 +68,8 @@ class GpuApi:
             "AADGpu_SynthLut": (None, [vp]),
             "AADGpu_SetKernelPath": (None, [C.c_int]),
             "AADGpu_SetEncoderPairing": (None, [C.c_int]),
+            "AADGpu_SetEncodeSegmentBlocks": (C.c_int, [C.c_void_p, C.c_uint32]),
+            "AADGpu_GetEncodeSegmentBlocks": (C.c_uint32, [C.c_void_p]),
             "AADGpu_EncodeInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, u32, C.POINTER(u32)]),
             "AADGpu_DecodeInterleaved16": (C.c_int, [vp, vp, u32, vp, u32]),
             "AADGpu_ReconstructInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, C.POINTER(u32)]),

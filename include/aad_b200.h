@@ -58,6 +58,20 @@ void AADGpu_SetKernelPath(int path);
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */
 void AADGpu_SetEncoderPairing(int on);
 
+/* Segment-parallel encoding -- an EXTENSION, NOT byte-identical to the reference encoder.
+ * The reference carries the predictor weights and the step index from block to block through the whole stream
+ * (src/aad_encoder.c:21,853-886), which makes one stream a serial chain: a 1-hour stereo file is 2 GPU threads.
+ * With blocks > 0 every run of `blocks` consecutive blocks is encoded as if it were a stream of its own (zero
+ * weights and step index at its first block, no previous-block trial pass there: exactly what the reference does
+ * at the start of a stream), so a stream becomes ceil(num_blocks / blocks) independent chains per channel.
+ * The result is a valid .aad stream: every block header carries the chain state the decoder needs, so the stock
+ * decoder (and this library's) decodes it; each segment's bytes equal the reference encoder's output for that
+ * run of samples on a fresh handle.  Applies to AADGpu_EncodeBatch[Device], AADGpu_ReconstructBatch,
+ * AADGpu_EncodeInterleaved16 and AADGpu_ReconstructInterleaved16 on this context; never to the drop-in
+ * AADEncoder_EncodeWhole, which stays bit-exact with the reference.  0 (default) = off. */
+AADApiResult AADGpu_SetEncodeSegmentBlocks(struct AADGpu *gpu, uint32_t blocks);
+uint32_t AADGpu_GetEncodeSegmentBlocks(const struct AADGpu *gpu);
+
 /* Bind the calling host thread to the CPUs next to the device (the NUMA node of its PCIe root, from
  * sysfs).  Buffers the thread pins afterwards live on that node, so one device's copies do not cross
  * the socket interconnect.  Returns the number of CPUs in the set, 0 when the topology is unknown

@@ -134,3 +134,34 @@ def test_config4_thirty_minutes_eight_channels_properties(product, gpu_ctx, orac
     step = 1 << 20
     err2 = sum(float(np.sum((pcm[:, i:i + step].astype(np.float64) - dec[:, i:i + step]) ** 2)) for i in range(0, n, step))
     assert np.sqrt(err2 / (ch * n)) / 32767.0 < 6.0e-2
+
+
+@pytest.mark.parametrize("config", ["config3", "config4"])
+def test_long_streams_encode_in_parallel_with_segments(product, gpu_ctx, oracle, config):
+    """The extension that makes ONE long stream a parallel encode (AADGpu_SetEncodeSegmentBlocks; not byte-identical
+    to the reference encoder, tests/test_gpu_segments.py): configs 3 and 4 at full size with the CLI's 2 trials.
+    Sampled segments are compared with the oracle's encode of the same samples on a fresh handle, the whole stream
+    is decoded (block-parallel) and the round trip held to the reference's own tolerance."""
+    _, gpu = product
+    ch, rate, bits, n, spb, bs = (2, 48000, 4, 172_800_000, 992, 1024) if config == "config3" else (8, 96000, 3, 172_800_000, 292, 1008)
+    seg_blocks, trials = 64, 2
+    assert gpu.lib.AADGpu_SetEncodeSegmentBlocks(gpu_ctx, seg_blocks) == OK
+    try:
+        pcm, data, dec, (t_enc, t_dec) = run_stream(gpu, gpu_ctx, ch, rate, bits, n, trials=trials)
+    finally:
+        gpu.lib.AADGpu_SetEncodeSegmentBlocks(gpu_ctx, 0)
+    nblocks = (n + spb - 1) // spb
+    nseg = (nblocks + seg_blocks - 1) // seg_blocks
+    print(f"\n{config} on one B200, segments of {seg_blocks} blocks ({nseg * ch} chains), {trials} trials: encode {t_enc * 1e3:.1f} ms = "
+          f"{ch * n / t_enc / 1e6:.0f} Msamples/s, decode {t_dec * 1e3:.1f} ms")
+    rng = np.random.default_rng(9)
+    for k in sorted(set([0, 1, nseg - 2, nseg - 1] + rng.integers(0, nseg, size=60).tolist())):
+        s0 = k * seg_blocks * spb
+        rc, want = oracle.encode(pcm[:, s0:s0 + seg_blocks * spb], rate, bits, 1024, False, trials)
+        assert rc == 0
+        b0 = 31 + k * seg_blocks * bs
+        assert data[b0:b0 + len(want) - 31].tobytes() == want[31:], k
+    assert len(data) == 31 + (nblocks - 1) * bs + (aad_tail_bytes(n, spb, ch, bits) or bs)
+    step = 1 << 20
+    err2 = sum(float(np.sum((pcm[:, i:i + step].astype(np.float64) - dec[:, i:i + step]) ** 2)) for i in range(0, n, step))
+    assert np.sqrt(err2 / (ch * n)) / 32767.0 < 6.0e-2
