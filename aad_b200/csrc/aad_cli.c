@@ -299,6 +299,8 @@ static int execute_information(const char *name)
   return 0;
 }
 
+static struct AADGpuGroup *g_group = NULL;   /* set when --device names more than one GPU */
+
 static int execute_encode(struct AADGpu *gpu, const char *in_name, const char *out_name, const struct AADEncodeParameter *cli)
 {
   struct wav_input w;
@@ -315,7 +317,11 @@ static int execute_encode(struct AADGpu *gpu, const char *in_name, const char *o
   uint32_t out_size = 0;
   int rc = 1;
   if (data != NULL) {
-    const AADApiResult r = AADGpu_EncodeInterleaved16(gpu, &prm, w.pcm16, w.info.num_samples, data, (uint32_t)bound, &out_size);
+    /* several devices share ONE file's encode only in segment mode (--segment-blocks); otherwise device 0 does it */
+    const uint32_t seg = AADGpu_GetEncodeSegmentBlocks(gpu);
+    const AADApiResult r = (g_group != NULL && seg != 0)
+        ? AADGpuGroup_EncodeInterleaved16(g_group, &prm, seg, w.pcm16, w.info.num_samples, data, (uint32_t)bound, &out_size)
+        : AADGpu_EncodeInterleaved16(gpu, &prm, w.pcm16, w.info.num_samples, data, (uint32_t)bound, &out_size);
     if (r != AAD_APIRESULT_OK) fprintf(stderr, "Failed to encode. API result:%d %s\n", r, AADGpu_LastError());
     else rc = write_file(out_name, data, out_size);
     io_free(data);
@@ -323,8 +329,6 @@ static int execute_encode(struct AADGpu *gpu, const char *in_name, const char *o
   wav_input_release(&w);
   return rc;
 }
-
-static struct AADGpuGroup *g_group = NULL;   /* set when --device names more than one GPU */
 
 static int execute_decode(struct AADGpu *gpu, const char *in_name, const char *out_name)
 {

@@ -983,7 +983,7 @@ static void split_range(uint64_t n, int parts, int index, uint64_t *begin, uint6
   *end = *begin + base + (i < extra ? 1u : 0u);
 }
 
-enum group_op { GROUP_ENCODE_BATCH, GROUP_DECODE_BATCH, GROUP_DECODE_STREAM };
+enum group_op { GROUP_ENCODE_BATCH, GROUP_DECODE_BATCH, GROUP_DECODE_STREAM, GROUP_ENCODE_STREAM };
 
 struct group_task {
   enum group_op op;
@@ -998,6 +998,9 @@ struct group_task {
   /* GROUP_DECODE_STREAM */
   struct AADHeaderInfo header;
   uint32_t data_size, block_begin, block_end;
+  /* GROUP_ENCODE_STREAM */
+  struct AADEncodeParameter param;
+  uint32_t num_samples, segment_blocks;
   int bind;
   AADApiResult result;
   char error[320];
@@ -1005,6 +1008,10 @@ struct group_task {
 
 static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
                                         uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved);
+
+static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
+                                        const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
+                                        uint8_t *data);
 
 static void *group_worker(void *arg)
 {
@@ -1016,6 +1023,10 @@ static void *group_worker(void *arg)
       break;
     case GROUP_DECODE_BATCH:
       t->result = AADGpu_DecodeBatch(t->gpu, &t->batch, t->aad_in, t->lens, t->pcm_out);
+      break;
+    case GROUP_ENCODE_STREAM:
+      t->result = encode_stream_range(t->gpu, &t->param, t->segment_blocks, t->pcm_in, t->num_samples, t->block_begin,
+                                      t->block_end, t->aad_out);
       break;
     default:
       t->result = decode_stream_range(t->gpu, &t->header, t->aad_in, t->data_size, t->block_begin, t->block_end, t->pcm_out);
@@ -1182,4 +1193,104 @@ AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_
     t->pcm_out = interleaved;
   }
   return n ? group_run(tasks, n) : AAD_APIRESULT_OK;
+}
+
+/* ---- one stream ENCODED by a group: segment mode only ------------------------------------------- */
+
+/* blocks [b0, b1) of one stream (b0 on a segment boundary) from interleaved samples [b0*spb, min(b1*spb, ns)):
+ * the shard copies only its own samples, encodes its segments as independent chains and writes its own byte
+ * range of the caller's stream (the 31-byte file header with block 0) */
+static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
+                                        const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
+                                        uint8_t *data)
+{
+  struct aadf_geometry geo;
+  const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  const uint32_t C = geo.channels, spb = geo.samples_per_block, bs = geo.block_size, ns = num_samples;
+  const uint32_t nblk = aadf_num_blocks(ns, spb);
+  const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < ns) ? (uint64_t)b1 * spb : ns;
+  if (b1 <= b0 || s1 <= s0) return AAD_APIRESULT_OK;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  const uint64_t count = s1 - s0;
+  const uint64_t pitch = round_up64(count, 64);
+  const uint64_t byte0 = AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
+  const uint64_t total = aadf_stream_bytes(ns, C, geo.bits, bs, spb);
+  uint64_t byte1 = AADF_FILE_HEADER_BYTES + (uint64_t)b1 * bs;
+  if (byte1 > total) byte1 = total;
+  const uint64_t span = byte1 - byte0;
+  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * count * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + (size_t)bs + 256)) return AAD_APIRESULT_NG;
+  cudaStream_t s = gpu->s_run;
+  CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved + s0 * C, (size_t)C * count * 2, cudaMemcpyHostToDevice, s), "H2D wav shard");
+  CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, (uint32_t)count, s),
+     "deinterleave kernel launch");
+  CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)span + (size_t)bs + 256, s), "memset aad");
+  /* the shard's first block 32-byte aligned at ptr + 32, the file header (shard 0 only) right in front of it;
+   * the kernel addresses block b at aad + 31 + b*block_size and sample i of a row at pcm + i, so both bases are
+   * shifted back to absolute indexing (only ever dereferenced inside the shard) */
+  uint8_t *d_block0 = (uint8_t *)gpu->aad.ptr + 32;
+  struct aadk_encode_params p;
+  memset(&p, 0, sizeof(p));
+  p.pcm = (const int16_t *)gpu->pcm.ptr - s0;
+  p.pcm_clip_stride = 0;
+  p.pcm_ch_stride = pitch;
+  p.uniform_samples = ns;
+  p.num_streams = 1;
+  p.geo = geo;
+  p.sampling_rate = prm->sampling_rate;
+  p.trials = prm->num_encode_trials;
+  p.aad = d_block0 - byte0;
+  p.aad_stride = 0;
+  p.block_begin = b0;
+  p.block_end = b1;
+  p.segment_blocks = segment_blocks;
+  p.num_segments = (nblk + segment_blocks - 1) / segment_blocks;
+  CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
+  const uint64_t lead = (b0 == 0) ? AADF_FILE_HEADER_BYTES : 0;
+  CU(cudaMemcpyAsync(data + byte0 - lead, d_block0 - lead, (size_t)(span + lead), cudaMemcpyDeviceToHost, s), "D2H aad shard");
+  CU(cudaStreamSynchronize(s), "sync");
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpuGroup_EncodeInterleaved16(struct AADGpuGroup *g, const struct AADEncodeParameter *prm,
+                                             uint32_t segment_blocks, const int16_t *interleaved, uint32_t num_samples,
+                                             uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+  if (!g || !prm || !interleaved || !data || !output_size) return AAD_APIRESULT_INVALID_ARGUMENT;
+  if (segment_blocks == 0) {
+    aadgpu_set_error("one stream cannot be encoded in shards bit-exactly (the reference carries the chain state through the "
+                     "whole stream, src/aad_encoder.c:853-886): pass segment_blocks > 0 (AADGpu_SetEncodeSegmentBlocks)");
+    return AAD_APIRESULT_INVALID_ARGUMENT;
+  }
+  struct aadf_geometry geo;
+  const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (data_size < AADF_FILE_HEADER_BYTES) return AAD_APIRESULT_INSUFFICIENT_DATA;
+  const uint64_t bytes = aadf_stream_bytes(num_samples, geo.channels, geo.bits, geo.block_size, geo.samples_per_block);
+  if (bytes > data_size) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  const uint32_t nblk = aadf_num_blocks(num_samples, geo.samples_per_block);
+  const uint64_t nseg = ((uint64_t)nblk + segment_blocks - 1) / segment_blocks;
+  struct group_task tasks[AADGPU_MAX_GROUP];
+  int n = 0;
+  for (int d = 0; d < g->size; d++) {
+    uint64_t g0, g1;
+    split_range(nseg, g->size, d, &g0, &g1);
+    if (g1 == g0) continue;
+    struct group_task *t = &tasks[n++];
+    memset(t, 0, sizeof(*t));
+    t->op = GROUP_ENCODE_STREAM;
+    t->gpu = g->gpu[d];
+    t->param = *prm;
+    t->segment_blocks = segment_blocks;
+    t->pcm_in = interleaved;
+    t->num_samples = num_samples;
+    t->block_begin = (uint32_t)(g0 * segment_blocks);
+    t->block_end = (uint32_t)((g1 * segment_blocks < nblk) ? g1 * segment_blocks : nblk);
+    t->aad_out = data;
+  }
+  const AADApiResult e = n ? group_run(tasks, n) : AAD_APIRESULT_OK;
+  if (e == AAD_APIRESULT_OK) *output_size = (uint32_t)bytes;
+  return e;
 }

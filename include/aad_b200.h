@@ -153,6 +153,14 @@ AADApiResult AADGpuGroup_DecodeBatch(struct AADGpuGroup *group, const struct AAD
                                      const uint8_t *aad, const uint32_t *sizes, int16_t *pcm);
 AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *group, const uint8_t *data, uint32_t data_size,
                                              int16_t *interleaved, uint32_t capacity_samples);
+/* ONE stream encoded by the whole group -- segment mode only (see AADGpu_SetEncodeSegmentBlocks: an extension,
+ * not byte-identical to the reference encoder): the segments are shared out in contiguous ranges, each device
+ * copies only its own samples and writes its own byte range of `data`.  Same bytes as AADGpu_EncodeInterleaved16
+ * on one device with the same segment_blocks.  segment_blocks == 0 is refused with AAD_APIRESULT_INVALID_ARGUMENT:
+ * without segments a stream is a serial chain (src/aad_encoder.c:853-886) and does not shard. */
+AADApiResult AADGpuGroup_EncodeInterleaved16(struct AADGpuGroup *group, const struct AADEncodeParameter *param,
+                                             uint32_t segment_blocks, const int16_t *interleaved, uint32_t num_samples,
+                                             uint8_t *data, uint32_t data_size, uint32_t *output_size);
 
 /* ---- deterministic synthetic PCM (bench / tests), SURVEY.md 8(d) ------------------------ */
 AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,

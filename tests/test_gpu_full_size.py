@@ -165,3 +165,28 @@ def test_long_streams_encode_in_parallel_with_segments(product, gpu_ctx, oracle,
     step = 1 << 20
     err2 = sum(float(np.sum((pcm[:, i:i + step].astype(np.float64) - dec[:, i:i + step]) ** 2)) for i in range(0, n, step))
     assert np.sqrt(err2 / (ch * n)) / 32767.0 < 6.0e-2
+    if config == "config3":
+        # the same stream from host memory (WAV order), its segments shared out over a device group: what
+        # `aad -e --segment-blocks 64 --device ...` does; identical bytes to the one-device encode above
+        prm = make_param(ch, rate, bits, 1024, False, trials)
+        inter = gpu.pinned((n, ch), np.int16)
+        inter[:] = pcm.T
+        blob = gpu.pinned((len(data) + 64,), np.uint8)
+        for shards in (1, 4):
+            devices = device_list(gpu, shards)
+            g = gpu.lib.AADGpuGroup_Create((C.c_int * len(devices))(*devices), len(devices))
+            assert g, gpu.last_error()
+            try:
+                size = C.c_uint32(0)
+                t0 = time.perf_counter()
+                rc = gpu.lib.AADGpuGroup_EncodeInterleaved16(g, C.byref(prm), seg_blocks, inter.ctypes.data, n, blob.ctypes.data,
+                                                             len(blob), C.byref(size))
+                dt = time.perf_counter() - t0
+                assert rc == OK, gpu.last_error()
+                assert size.value == len(data) and np.array_equal(blob[:size.value], data), shards
+                print(f"config3 encode from host memory in {shards} segment-range shard(s) on {gpu.device_count()} GPU(s): {dt * 1e3:.0f} ms "
+                      f"= {ch * n / dt / 1e6:.0f} Msamples/s end to end")
+            finally:
+                gpu.lib.AADGpuGroup_Destroy(g)
+        gpu.free_pinned(inter)
+        gpu.free_pinned(blob)

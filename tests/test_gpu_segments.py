@@ -124,3 +124,61 @@ def test_cli_segment_blocks_output_decodes_with_the_reference_cli(product, gpu_c
     p, _ = aadtest.read_wav16(tmp_path / "plain_ref.wav")
     rms = lambda e: float(np.sqrt(np.mean(e.astype(np.float64) ** 2)))
     assert rms(a - x) < 1.5 * rms(p - x) + 1.0
+
+
+def _device_sets(gpu):
+    sets = [[0], [0, 0], [0, 0, 0]]
+    if gpu.device_count() >= 2:
+        sets.append(list(range(min(gpu.device_count(), 8))))
+    return sets
+
+
+@pytest.mark.parametrize("bits,channels,ms,block,seg_blocks", [(4, 2, False, 1024, 4), (3, 2, True, 1024, 1), (4, 1, False, 1024, 7),
+                                                               (2, 1, False, 333, 3), (3, 8, False, 1024, 5)])
+def test_one_stream_encodes_in_segment_range_shards(product, gpu_ctx, oracle, bits, channels, ms, block, seg_blocks):
+    """AADGpuGroup_EncodeInterleaved16: the segments of ONE stream shared out over the devices of a group (a device may
+    be named twice, so one GPU covers it) == the single-device segment encode == the oracle's fresh-handle encodes.
+    Also a stream with fewer segments than devices."""
+    _, gpu = product
+    prm = make_param(channels, 48000, bits, block, ms, 2)
+    for n in (150001, 700):
+        pcm = aadtest.signal("music", channels, n, bits)
+        inter = np.ascontiguousarray(pcm.T)
+        want = _segmented_reference(oracle, pcm, 48000, bits, block, ms, 2, seg_blocks)
+        cap = len(want) + 64
+        for devices in _device_sets(gpu):
+            arr = (C.c_int * len(devices))(*devices)
+            g = gpu.lib.AADGpuGroup_Create(arr, len(devices))
+            assert g, gpu.last_error()
+            try:
+                data = np.full(cap, 0xAB, dtype=np.uint8)
+                size = C.c_uint32(0)
+                rc = gpu.lib.AADGpuGroup_EncodeInterleaved16(g, C.byref(prm), seg_blocks, inter.ctypes.data, n, data.ctypes.data, cap, C.byref(size))
+                assert rc == OK, gpu.last_error()
+                assert size.value == len(want) and data[:size.value].tobytes() == want, (n, devices)
+                assert (data[size.value:] == 0xAB).all()
+                # refused without segments: one stream is a serial chain
+                assert gpu.lib.AADGpuGroup_EncodeInterleaved16(g, C.byref(prm), 0, inter.ctypes.data, n, data.ctypes.data, cap, C.byref(size)) == 1
+                assert "segment_blocks" in gpu.last_error()
+                assert gpu.lib.AADGpuGroup_EncodeInterleaved16(g, C.byref(prm), seg_blocks, inter.ctypes.data, n, data.ctypes.data, 40, C.byref(size)) == 3
+            finally:
+                gpu.lib.AADGpuGroup_Destroy(g)
+    # the single-device call with the context setting gives the same bytes
+    assert gpu.lib.AADGpu_SetEncodeSegmentBlocks(gpu_ctx, seg_blocks) == OK
+    try:
+        data = np.zeros(cap, dtype=np.uint8)
+        size = C.c_uint32(0)
+        assert gpu.lib.AADGpu_EncodeInterleaved16(gpu_ctx, C.byref(prm), inter.ctypes.data, n, data.ctypes.data, cap, C.byref(size)) == OK
+        assert data[:size.value].tobytes() == want
+    finally:
+        gpu.lib.AADGpu_SetEncodeSegmentBlocks(gpu_ctx, 0)
+
+
+def test_cli_segment_encode_on_a_device_list(tmp_path):
+    cli = aadtest.ROOT / "aad_b200" / "aad"
+    src = aadtest.GOLDEN / "pi_15-25sec.wav"
+    one, many = tmp_path / "one.aad", tmp_path / "many.aad"
+    for out, dev in ((one, "0"), (many, "0,0,0")):
+        r = subprocess.run([str(cli), "-e", "-S", "6", "--device", dev, str(src), str(out)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+    assert one.read_bytes() == many.read_bytes()
