@@ -366,55 +366,36 @@ static int execute_decode(struct AADGpu *gpu, const char *in_name, const char *o
 static int execute_analysis(struct AADGpu *gpu, int mode, const char *in_name, const char *out_name,
                             const struct AADEncodeParameter *cli)
 {
+  /* src/main.c:275-503: the data chunk goes to the device as it lies in the file; narrowing to 16 bits, encode,
+   * decode and the per-sample arithmetic of the mode run there (AADGpu_AnalyzeWav) */
   struct wav_input w;
   struct AADEncodeParameter prm;
   if (wav_input_open(in_name, &w) != 0) return 1;
   fill_parameter(&prm, cli, &w.info);
-  const size_t count = (size_t)w.info.num_samples * w.info.num_channels;
-  int16_t *dec = (int16_t *)io_alloc(count * sizeof(int16_t));
+  const uint32_t bits = w.info.bits_per_sample, C = w.info.num_channels, n = w.info.num_samples;
+  const size_t count = (size_t)n * C;
+  const uint8_t *in_data = w.image + w.info.data_offset;
+  const size_t bytes = AADWAV_HEADER_BYTES + count * (bits / 8);
+  uint8_t *image = (mode == MODE_CALCULATE) ? NULL : (uint8_t *)io_alloc(bytes);
+  double stats[3] = { 0.0, 0.0, 0.0 };
   int rc = 1;
-  if (dec == NULL) { wav_input_release(&w); return 1; }
-  const AADApiResult r = AADGpu_ReconstructInterleaved16(gpu, &prm, w.pcm16, w.info.num_samples, dec, NULL);
+  if (mode != MODE_CALCULATE && image == NULL) { wav_input_release(&w); return 1; }
+  const enum AADGpuAnalysis what = (mode == MODE_CALCULATE) ? AADGPU_ANALYSIS_STATISTICS
+                                 : (mode == MODE_GAP) ? AADGPU_ANALYSIS_RESIDUAL : AADGPU_ANALYSIS_RECONSTRUCT;
+  const AADApiResult r = AADGpu_AnalyzeWav(gpu, &prm, in_data, bits, n, what, image ? image + AADWAV_HEADER_BYTES : NULL, stats, NULL);
   if (r == AAD_APIRESULT_INVALID_FORMAT) {
     fprintf(stderr, "Failed to set encode parameter. Please check encode parameter. \n");
   } else if (r != AAD_APIRESULT_OK) {
     fprintf(stderr, "Failed to encode. API result:%d %s\n", r, AADGpu_LastError());
+  } else if (mode == MODE_CALCULATE) {
+    printf("RMSE:%f MSD:%f MaxAE:%f \n", stats[0], stats[1], stats[2]);   /* src/main.c:492-495 */
+    rc = 0;
   } else {
-    const uint8_t *in_data = w.image + w.info.data_offset;
-    const uint32_t bits = w.info.bits_per_sample, C = w.info.num_channels, n = w.info.num_samples;
-    if (mode == MODE_CALCULATE) {
-      /* src/main.c:470-497, summed channel by channel like the reference */
-      double rms = 0.0, abs_sum = 0.0, max_err = 0.0;
-      for (uint32_t c = 0; c < C; c++) {
-        for (uint32_t s = 0; s < n; s++) {
-          const size_t i = (size_t)s * C + c;
-          const int32_t residual = (int32_t)((uint32_t)aadwav_sample32(in_data, bits, i) - ((uint32_t)(int32_t)dec[i] << 16));
-          const double pcm1 = (double)residual / INT32_MAX, pcm2 = (double)dec[i] / INT32_MAX;
-          rms += pow(pcm1 - pcm2, 2);
-          abs_sum += fabs(pcm1 - pcm2);
-          if (max_err < fabs(pcm1 - pcm2)) max_err = fabs(pcm1 - pcm2);
-        }
-      }
-      printf("RMSE:%f MSD:%f MaxAE:%f \n", sqrt(rms / ((double)C * n)), abs_sum / ((double)C * n), max_err);
-      rc = 0;
-    } else {
-      /* the output keeps the input's format: src/main.c:372-381, :418-428 */
-      const size_t bytes = AADWAV_HEADER_BYTES + count * (bits / 8);
-      uint8_t *image = (uint8_t *)io_alloc(bytes);
-      if (image != NULL) {
-        aadwav_write_header(image, C, w.info.sampling_rate, bits, n);
-        uint8_t *out_data = image + AADWAV_HEADER_BYTES;
-        for (size_t i = 0; i < count; i++) {
-          const uint32_t recon = (uint32_t)(int32_t)dec[i] << 16;
-          const uint32_t v = (mode == MODE_GAP) ? (uint32_t)aadwav_sample32(in_data, bits, i) - recon : recon;
-          aadwav_store32(out_data, bits, i, (int32_t)v);
-        }
-        rc = write_file(out_name, image, bytes);
-        io_free(image);
-      }
-    }
+    /* the output keeps the input's format: src/main.c:372-381, :418-428 */
+    aadwav_write_header(image, C, w.info.sampling_rate, bits, n);
+    rc = write_file(out_name, image, bytes);
   }
-  io_free(dec);
+  if (image != NULL) io_free(image);
   wav_input_release(&w);
   return rc;
 }

@@ -92,7 +92,7 @@ void AADGpu_Destroy(struct AADGpu *g)
   if (!g) return;
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
-  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut, &g->wav, &g->pcm2 };
+  struct aadgpu_buffer *bufs[] = { &g->pcm, &g->aad, &g->state, &g->lens, &g->sizes, &g->lut, &g->wav, &g->pcm2, &g->raw, &g->stats };
   for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
     if (bufs[i]->ptr) cudaFree(bufs[i]->ptr);
   for (int i = 0; i < AADGPU_MAX_SLICES; i++) {
@@ -782,13 +782,15 @@ static AADApiResult encode_interleaved_device(struct AADGpu *gpu, const struct A
   const uint64_t pitch = round_up64(num_samples, 64);
   const uint64_t bytes = aadf_stream_bytes(num_samples, C, geo->bits, geo->block_size, geo->samples_per_block);
   const uint64_t bound = aadf_stream_bytes_bound(num_samples, geo->block_size, geo->samples_per_block);
-  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * num_samples * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
   cudaStream_t s = gpu->s_run;
-  CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved, (size_t)C * num_samples * 2, cudaMemcpyHostToDevice, s), "H2D wav");
-  CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s),
-     "deinterleave kernel launch");
+  if (interleaved != NULL) {   /* NULL: the caller has put the planar samples into gpu->pcm already (same pitch) */
+    if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * num_samples * 2)) return AAD_APIRESULT_NG;
+    CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved, (size_t)C * num_samples * 2, cudaMemcpyHostToDevice, s), "H2D wav");
+    CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s),
+       "deinterleave kernel launch");
+  }
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)bound + 128, s), "memset aad");
   struct aadk_encode_params p;
   memset(&p, 0, sizeof(p));
@@ -926,6 +928,79 @@ AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AA
   CU(cudaMemcpyAsync(reconstructed, gpu->wav.ptr, (size_t)geo.channels * num_samples * 2, cudaMemcpyDeviceToHost, gpu->s_run),
      "D2H wav");
   CU(cudaStreamSynchronize(gpu->s_run), "sync");
+  if (encoded_size) *encoded_size = (uint32_t)bytes;
+  return AAD_APIRESULT_OK;
+}
+
+/* ---- the analysis modes of the command line, src/main.c:275-503, with the samples staying on the device -------- */
+
+static void header_of(const struct AADEncodeParameter *prm, const struct aadf_geometry *geo, uint32_t num_samples,
+                      struct AADHeaderInfo *h)
+{
+  memset(h, 0, sizeof(*h));
+  h->num_channels = (uint16_t)geo->channels;
+  h->num_samples = num_samples;
+  h->sampling_rate = prm->sampling_rate;
+  h->bits_per_sample = (uint16_t)geo->bits;
+  h->block_size = (uint16_t)geo->block_size;
+  h->num_samples_per_block = geo->samples_per_block;
+  h->ch_process_method = prm->ch_process_method;
+}
+
+AADApiResult AADGpu_AnalyzeWav(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
+                               uint32_t wav_bits_per_sample, uint32_t num_samples, enum AADGpuAnalysis what,
+                               uint8_t *out_data, double stats[3], uint32_t *encoded_size)
+{
+  if (!gpu || !prm || !wav_data) return AAD_APIRESULT_INVALID_ARGUMENT;
+  if (what == AADGPU_ANALYSIS_STATISTICS ? stats == NULL : out_data == NULL) return AAD_APIRESULT_INVALID_ARGUMENT;
+  if (what != AADGPU_ANALYSIS_RECONSTRUCT && what != AADGPU_ANALYSIS_RESIDUAL && what != AADGPU_ANALYSIS_STATISTICS)
+    return AAD_APIRESULT_INVALID_ARGUMENT;
+  const uint32_t wb = wav_bits_per_sample;
+  if (wb != 8 && wb != 16 && wb != 24 && wb != 32) return AAD_APIRESULT_INVALID_FORMAT;   /* src/wav.c:222-238 */
+  struct aadf_geometry geo;
+  const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  const uint32_t C = geo.channels;
+  const uint64_t count = (uint64_t)C * num_samples;
+  const size_t raw_bytes = (size_t)count * (wb / 8);
+  const uint64_t in_pitch = round_up64(num_samples, 64);
+  if (!aadgpu_reserve(gpu, &gpu->raw, raw_bytes)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * in_pitch * 2)) return AAD_APIRESULT_NG;
+  cudaStream_t s = gpu->s_run;
+  /* the data chunk goes up as it lies in the file; narrowing to 16 bits and de-interleaving in one kernel */
+  CU(cudaMemcpyAsync(gpu->raw.ptr, wav_data, raw_bytes, cudaMemcpyHostToDevice, s), "H2D wav data");
+  CU((cudaError_t)aadk_launch_wav_to_planar16((const uint8_t *)gpu->raw.ptr, wb, (int16_t *)gpu->pcm.ptr, in_pitch, C, num_samples, s),
+     "wav_to_planar16 kernel launch");
+  uint64_t pitch = 0, bytes = 0;
+  AADApiResult e = encode_interleaved_device(gpu, prm, &geo, NULL, num_samples, &pitch, &bytes);
+  if (e != AAD_APIRESULT_OK) return e;
+  struct AADHeaderInfo h;
+  header_of(prm, &geo, num_samples, &h);
+  e = decode_to_interleaved_device(gpu, &h, (const uint8_t *)gpu->aad.ptr + 1, bytes);   /* -> gpu->wav, interleaved int16 */
+  if (e != AAD_APIRESULT_OK) return e;
+  if (what == AADGPU_ANALYSIS_STATISTICS) {
+    double partials[3 * AADK_STATS_BLOCKS];
+    if (!aadgpu_reserve(gpu, &gpu->stats, sizeof(partials))) return AAD_APIRESULT_NG;
+    CU((cudaError_t)aadk_launch_analysis_stats((const uint8_t *)gpu->raw.ptr, wb, (const int16_t *)gpu->wav.ptr, count,
+                                               (double *)gpu->stats.ptr, s), "analysis_stats kernel launch");
+    CU(cudaMemcpyAsync(partials, gpu->stats.ptr, sizeof(partials), cudaMemcpyDeviceToHost, s), "D2H partial sums");
+    CU(cudaStreamSynchronize(s), "sync");
+    double sq = 0.0, ab = 0.0, mx = 0.0;
+    for (int b = 0; b < AADK_STATS_BLOCKS; b++) {
+      sq += partials[3 * b];
+      ab += partials[3 * b + 1];
+      if (mx < partials[3 * b + 2]) mx = partials[3 * b + 2];
+    }
+    stats[0] = sqrt(sq / (double)count);    /* RMSE, src/main.c:492-494 */
+    stats[1] = ab / (double)count;          /* MSD */
+    stats[2] = mx;                          /* MaxAE */
+  } else {
+    CU((cudaError_t)aadk_launch_analysis_image((uint8_t *)gpu->raw.ptr, wb, (const int16_t *)gpu->wav.ptr, count,
+                                               what == AADGPU_ANALYSIS_RESIDUAL, s), "analysis_image kernel launch");
+    CU(cudaMemcpyAsync(out_data, gpu->raw.ptr, raw_bytes, cudaMemcpyDeviceToHost, s), "D2H wav data");
+    CU(cudaStreamSynchronize(s), "sync");
+  }
   if (encoded_size) *encoded_size = (uint32_t)bytes;
   return AAD_APIRESULT_OK;
 }

@@ -25,7 +25,7 @@ struct AADGpu {
   int device;
   cudaStream_t s_in, s_run, s_out;
   cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES];
-  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2;
+  struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2, raw, stats;
   int lut_ready;
   uint32_t segment_blocks;   /* AADGpu_SetEncodeSegmentBlocks; 0 = the reference's whole-stream state carry */
 };

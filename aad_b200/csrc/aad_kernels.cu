@@ -449,6 +449,93 @@ __global__ void aad_widen16(const int16_t *__restrict__ in, uint64_t in_pitch, i
   out[r * out_pitch + i] = (int32_t)in[r * in_pitch + i];
 }
 
+/* ------------------------------------------------------------------------------------------
+ * WAV sample formats and the analysis modes of the command line (src/main.c:275-503) on the device
+ * ------------------------------------------------------------------------------------------ */
+
+/* sample i (interleaved order) of a WAV data chunk, widened to 32 bits left justified: src/wav.c:391-415 */
+__device__ __forceinline__ int32_t wav_sample32(const uint8_t *data, uint32_t bits, uint64_t i)
+{
+  switch (bits) {
+    case 8:  return (int32_t)(((uint32_t)data[i] - 128u) << 24);
+    case 16: return (int32_t)((uint32_t)reinterpret_cast<const uint16_t *>(data)[i] << 16);
+    case 24: return (int32_t)(((uint32_t)data[3 * i] | ((uint32_t)data[3 * i + 1] << 8) | ((uint32_t)data[3 * i + 2] << 16)) << 8);
+    default: return (int32_t)reinterpret_cast<const uint32_t *>(data)[i];
+  }
+}
+
+/* the matching narrowing store: src/wav.c:418-436 */
+__device__ __forceinline__ void wav_store32(uint8_t *data, uint32_t bits, uint64_t i, int32_t v)
+{
+  switch (bits) {
+    case 8:  data[i] = (uint8_t)((v >> 24) + 128); break;
+    case 16: reinterpret_cast<uint16_t *>(data)[i] = (uint16_t)(v >> 16); break;
+    case 24: {
+      const uint32_t u = (uint32_t)(v >> 8);
+      data[3 * i] = (uint8_t)u; data[3 * i + 1] = (uint8_t)(u >> 8); data[3 * i + 2] = (uint8_t)(u >> 16);
+      break;
+    }
+    default: reinterpret_cast<uint32_t *>(data)[i] = (uint32_t)v; break;
+  }
+}
+
+/* (int16_t)(PCM >> 16) of every sample, interleaved -> planar: src/main.c:175-179 for any WAV bit depth */
+__global__ void aad_wav_to_planar16(const uint8_t *__restrict__ data, uint32_t bits, int16_t *__restrict__ planar,
+                                    uint64_t ch_stride, uint32_t channels, uint32_t num_samples)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)channels * num_samples) return;
+  const uint32_t s = (uint32_t)(t / channels), c = (uint32_t)(t % channels);
+  planar[(uint64_t)c * ch_stride + s] = (int16_t)(wav_sample32(data, bits, t) >> 16);
+}
+
+/* -r: the reconstruction, -g: input minus reconstruction (32-bit wrapping, src/main.c:372-381, :418-428), written
+ * over the input in the input's own sample format */
+__global__ void aad_analysis_image(uint8_t *data, uint32_t bits, const int16_t *__restrict__ decoded, uint64_t count, int gap)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t recon = (uint32_t)(int32_t)decoded[i] << 16;
+  const uint32_t v = gap ? (uint32_t)wav_sample32(data, bits, i) - recon : recon;
+  wav_store32(data, bits, i, (int32_t)v);
+}
+
+/* -c, src/main.c:470-497: per sample pcm1 = residual / INT32_MAX, pcm2 = reconstruction / INT32_MAX (both double),
+ * sums of (pcm1 - pcm2)^2 and |pcm1 - pcm2| and their maximum.  Every thread strides over the samples, a block reduces
+ * in a fixed tree, the host adds the per-block partials in order: deterministic, but not the reference's sample-by-
+ * sample summation order (the sums agree to ~1e-15 relative; the maximum is exact). */
+constexpr int kStatsThreads = 256;
+__global__ void __launch_bounds__(kStatsThreads) aad_analysis_stats(const uint8_t *__restrict__ data, uint32_t bits,
+                                                                   const int16_t *__restrict__ decoded, uint64_t count,
+                                                                   double *__restrict__ partials)
+{
+  __shared__ double sh[3][kStatsThreads];
+  double sq = 0.0, ab = 0.0, mx = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kStatsThreads + threadIdx.x; i < count; i += (uint64_t)gridDim.x * kStatsThreads) {
+    const int32_t dec = decoded[i];
+    const int32_t residual = (int32_t)((uint32_t)wav_sample32(data, bits, i) - ((uint32_t)dec << 16));
+    const double d = (double)residual / 2147483647.0 - (double)dec / 2147483647.0;
+    sq += d * d;
+    ab += fabs(d);
+    mx = fmax(mx, fabs(d));
+  }
+  sh[0][threadIdx.x] = sq; sh[1][threadIdx.x] = ab; sh[2][threadIdx.x] = mx;
+  __syncthreads();
+  for (int w = kStatsThreads / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
+      sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + w]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[3 * blockIdx.x + 0] = sh[0][0];
+    partials[3 * blockIdx.x + 1] = sh[1][0];
+    partials[3 * blockIdx.x + 2] = sh[2][0];
+  }
+}
+
 inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
 }  // namespace
@@ -548,6 +635,32 @@ int aadk_launch_narrow32(const int32_t *in, uint64_t in_pitch, int16_t *out, uin
 {
   if ((uint64_t)rows * n == 0) return 0;
   aad_narrow32<<<grid_for((uint64_t)rows * n, 256), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, n);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_wav_to_planar16(const uint8_t *data, uint32_t bits, int16_t *planar, uint64_t ch_stride, uint32_t channels,
+                                uint32_t num_samples, void *stream)
+{
+  const uint64_t n = (uint64_t)channels * num_samples;
+  if (n == 0) return 0;
+  aad_wav_to_planar16<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(data, bits, planar, ch_stride, channels, num_samples);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_analysis_image(uint8_t *data, uint32_t bits, const int16_t *decoded, uint64_t count, int gap, void *stream)
+{
+  if (count == 0) return 0;
+  aad_analysis_image<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(data, bits, decoded, count, gap);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_analysis_stats(const uint8_t *data, uint32_t bits, const int16_t *decoded, uint64_t count, double *partials,
+                               void *stream)
+{
+  aad_analysis_stats<<<AADK_STATS_BLOCKS, kStatsThreads, 0, (cudaStream_t)stream>>>(data, bits, decoded, count, partials);
   g_launches++;
   return (int)cudaGetLastError();
 }

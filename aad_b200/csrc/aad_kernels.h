@@ -93,6 +93,19 @@ int aadk_launch_narrow32(const int32_t *in, uint64_t in_pitch, int16_t *out, uin
 int aadk_launch_widen16(const int16_t *in, uint64_t in_pitch, int32_t *out, uint64_t out_pitch, uint32_t rows, uint64_t first,
                         uint64_t n, void *stream);
 
+/* WAV data chunk (8 / 16 / 24 / 32 bits per sample, interleaved) -> planar int16 rows: the (int16_t)(PCM >> 16) of
+ * src/main.c:175-179 with the widening of src/wav.c:391-415 */
+int aadk_launch_wav_to_planar16(const uint8_t *data, uint32_t bits, int16_t *planar, uint64_t ch_stride, uint32_t channels,
+                                uint32_t num_samples, void *stream);
+/* src/main.c:372-381 (-r) / :418-428 (-g): overwrite the WAV data chunk `data` (count samples) with the reconstruction
+ * `decoded` (interleaved int16) or with input minus reconstruction, in the chunk's own sample format */
+int aadk_launch_analysis_image(uint8_t *data, uint32_t bits, const int16_t *decoded, uint64_t count, int gap, void *stream);
+/* src/main.c:470-497 (-c): per-block partial sums {sum of squares, sum of magnitudes, maximum} of the reference's
+ * per-sample error term; partials holds 3 * AADK_STATS_BLOCKS doubles, to be added up in order on the host */
+#define AADK_STATS_BLOCKS 592
+int aadk_launch_analysis_stats(const uint8_t *data, uint32_t bits, const int16_t *decoded, uint64_t count, double *partials,
+                               void *stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t aadk_launch_count(void);
 /* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths;

@@ -162,6 +162,22 @@ AADApiResult AADGpuGroup_EncodeInterleaved16(struct AADGpuGroup *group, const st
                                              uint32_t segment_blocks, const int16_t *interleaved, uint32_t num_samples,
                                              uint8_t *data, uint32_t data_size, uint32_t *output_size);
 
+/* ---- the command line's analysis modes on the device, src/main.c:275-503 ------------------- */
+enum AADGpuAnalysis {
+  AADGPU_ANALYSIS_RECONSTRUCT = 0,   /* -r: encode -> decode, written in the input's sample format (src/main.c:372-381) */
+  AADGPU_ANALYSIS_RESIDUAL = 1,      /* -g: input minus reconstruction, 32-bit wrapping (src/main.c:418-428) */
+  AADGPU_ANALYSIS_STATISTICS = 2     /* -c: RMSE, MSD, MaxAE of src/main.c:470-497 */
+};
+/* wav_data: the data chunk of a PCM WAV file as it lies in the file (wav_bits_per_sample 8 / 16 / 24 / 32,
+ * num_samples per channel, interleaved).  The chunk is uploaded once; narrowing to the codec's 16 bits, the round
+ * trip, and the per-sample arithmetic of the mode all run on the device.  RECONSTRUCT / RESIDUAL write out_data
+ * (same size and format as wav_data); STATISTICS writes stats[0..2] = RMSE, MSD, MaxAE.  The two sums of STATISTICS
+ * are reduced in a fixed parallel order, not sample by sample as the reference does: they agree with the
+ * reference's to ~1e-15 relative (invisible at the command line's %f), MaxAE exactly.  encoded_size is optional. */
+AADApiResult AADGpu_AnalyzeWav(struct AADGpu *gpu, const struct AADEncodeParameter *param, const uint8_t *wav_data,
+                               uint32_t wav_bits_per_sample, uint32_t num_samples, enum AADGpuAnalysis what,
+                               uint8_t *out_data, double stats[3], uint32_t *encoded_size);
+
 /* ---- deterministic synthetic PCM (bench / tests), SURVEY.md 8(d) ------------------------ */
 AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                      uint32_t first_stream, int16_t *pcm_dev, void *stream);

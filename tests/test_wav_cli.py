@@ -279,6 +279,60 @@ def test_cli_reconstruct_gap_calculate(tmp_path, oracle, wavlib, bits):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bits,channels", [(8, 1), (16, 2), (24, 3), (32, 2)])
+def test_analyze_wav_api_against_numpy_model(product, gpu_ctx, oracle, bits, channels):
+    """AADGpu_AnalyzeWav on a data chunk long enough that every reduction thread sums many samples: -r / -g images
+    byte for byte, MaxAE exactly, the two sums of -c to 1e-12 relative (their order of summation is the one documented
+    difference from src/main.c:470-497)."""
+    import ctypes as C
+    from aad_b200.capi import make_param, OK
+    _, gpu = product
+    rng = np.random.default_rng(100 + bits)
+    n, rate = 700_001, 32000
+    base = aadtest.signal("music", channels, n, bits).T.astype(np.int64)         # [n, ch]
+    if bits == 8:
+        frames = (base >> 8) + 128
+        pcm32 = (frames - 128) << 24
+        raw = frames.astype(np.uint8).tobytes()
+    else:
+        frames = (base << (bits - 16)) + (rng.integers(0, 1 << (bits - 16), size=base.shape) if bits > 16 else 0)
+        pcm32 = frames << (32 - bits)
+        le = np.ascontiguousarray(frames.astype("<i8")).view(np.uint8).reshape(n, channels, 8)[:, :, :bits // 8]
+        raw = np.ascontiguousarray(le).tobytes()
+    pcm16 = (pcm32 >> 16).astype(np.int16).T
+    rc, data = oracle.encode(pcm16, rate, 3, 1024, False, 1)
+    rc2, dec, _ = oracle.decode(data)
+    assert rc == 0 and rc2 == 0
+    recon32 = dec.T.astype(np.int64) << 16
+    wrap = lambda v: ((v + (1 << 31)) % (1 << 32)) - (1 << 31)
+
+    def narrow(values32):                                                        # src/wav.c:418-436
+        v = wrap(values32) >> (32 - bits)
+        if bits == 8:
+            return ((v + 128) & 0xFF).astype(np.uint8).tobytes()
+        return np.ascontiguousarray(np.ascontiguousarray(v.astype("<i8")).view(np.uint8).reshape(n, channels, 8)[:, :, :bits // 8]).tobytes()
+
+    prm = make_param(channels, rate, 3, 1024, False, 1)
+    src = np.frombuffer(raw, dtype=np.uint8).copy()
+    out = np.zeros_like(src)
+    size = C.c_uint32(0)
+    assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 0, out.ctypes.data, None, C.byref(size)) == OK, gpu.last_error()
+    assert size.value == len(data) and out.tobytes() == narrow(recon32)
+    assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 1, out.ctypes.data, None, None) == OK
+    assert out.tobytes() == narrow(pcm32 - recon32)
+    stats = (C.c_double * 3)()
+    assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 2, None, stats, None) == OK
+    err = wrap(pcm32 - recon32) / 2147483647.0 - dec.T.astype(np.float64) / 2147483647.0
+    assert stats[2] == np.max(np.abs(err))
+    assert abs(stats[0] - np.sqrt(np.mean(err ** 2))) <= 1e-12 * stats[0]
+    assert abs(stats[1] - np.mean(np.abs(err))) <= 1e-12 * stats[1]
+    # argument checks
+    assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, 12, n, 0, out.ctypes.data, None, None) == 2     # INVALID_FORMAT
+    assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 2, None, None, None) == 1               # INVALID_ARGUMENT
+    assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 0, None, stats, None) == 1
+
+
+@pytest.mark.gpu
 def test_cli_differential_against_the_reference_cli(tmp_path):
     """Every mode, fixtures of the reference: same files, same stdout as the stock CLI run beside it."""
     if not REF_CLI.exists():
