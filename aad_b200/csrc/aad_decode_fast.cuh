@@ -119,7 +119,10 @@ struct DecChain {
   int32_t h0, h1, h2, h3;
   int32_t w0, w1, w2, w3;
   int32_t idx2;   /* kDecIdxScale * stepsize_index */
+  uint32_t four;  /* 4, opaque to the compiler (g_dec_four) */
 };
+
+__constant__ uint32_t g_dec_four = 4u;
 
 #if AAD_DEC_QTAB
 /* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
@@ -131,8 +134,10 @@ __device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const Dec
 #if AAD_DEC_QTAB == 2
   const uint32_t row = (uint32_t)c.idx2;
 #else
-  uint32_t row;    /* 4 * (index + 8) on the multiply pipe (the ALU pipe is the one this kernel saturates) */
-  asm("mad.lo.u32 %0, %1, 4, 32;" : "=r"(row) : "r"(c.idx2));
+  /* 4 * (index + 8) on the multiply pipe (the ALU pipe is the one this kernel saturates): the factor comes from
+   * constant memory, so ptxas cannot turn the multiply-add into an ALU-pipe LEA */
+  uint32_t row;
+  asm("mad.lo.u32 %0, %1, %2, 32;" : "=r"(row) : "r"(c.idx2), "r"(c.four));
 #endif
   uint32_t qoff;   /* (row & ~0x3C) | (x & 0x3C); bits 0-1 of row are zero */
   asm("lop3.b32 %0, %1, %2, 0x3C, 0xD8;" : "=r"(qoff) : "r"(row), "r"(x));
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
 
     DecChain c;
     c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+    c.four = g_dec_four;
 
     const uint32_t windows = (bs + G::TB - 1) / G::TB;
     uint4 pre[G::IN_LOADS];
@@ -552,6 +558,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
 
     DecChain c;
     c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+    c.four = g_dec_four;
 
     const uint32_t windows = (bs + TB - 1) / TB;
     const uint32_t gstride = GB * C;
