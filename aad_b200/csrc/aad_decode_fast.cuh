@@ -1,9 +1,9 @@
 /*
- * aad_decode_fast.cuh -- the production decoder kernel (included by aad_kernels.cu).
+ * aad_decode_fast.cuh -- the production decoder kernels (included by aad_kernels.cu).
  *
  * One thread = one (block, channel) chain (every block header reloads the whole chain state,
- * src/aad_decoder.c:364-380).  A warp owns 32/C consecutive blocks of one stream and walks them
- * in windows of 128 samples per chain:
+ * src/aad_decoder.c:364-380).  A warp task = 32/C consecutive blocks of one stream, walked in windows of
+ * 128 samples per chain:
  *
  *   global .aad  --16-byte coalesced loads (aligned superset, prefetched one window ahead)-->
  *   shared input rows --per-lane word reads + funnel shift (any byte alignment)--> sample chain
@@ -14,8 +14,11 @@
  * that a window never splits a code group and the block header (18*C bytes) plus, for mono, one
  * half step bring the read pointer back to word alignment.
  *
- * Tables: step size as uint16 indexed directly by the Q4 step index (the chain keeps 2*index =
- * the byte offset), index delta replicated per lane; both in shared memory.
+ * The grid is persistent: one wave of 16-warp CTAs (one per SM), every warp looping over its share of
+ * the warp tasks, so the shared-memory tables are built once per resident CTA.
+ *
+ * aad_decode_fast<BITS, C>  mono / stereo, sliding 32-bit words;
+ * aad_decode_wide<BITS>     any channel count (run time), byte reads from the shared input rows.
  */
 #pragma once
 
@@ -28,38 +31,20 @@ constexpr int kDecWarps = AAD_DEC_WARPS;
 constexpr int kDecWindow = 128;           /* samples per chain per window */
 constexpr int kDecOutPitch = 264;         /* 256 + 8: conflict-free 8-byte shared accesses */
 
-#ifndef AAD_DEC_QTAB
-#define AAD_DEC_QTAB 1
-#endif
 
-#if AAD_DEC_QTAB
 /* Dequantised difference per (step row, code) and index delta per magnitude, both in shared memory.
- * The chain keeps J = 4 * stepsize_index; the row of src/aad_tables.h:41 ((index + 8) >> 4) starts at byte
- * (J + 32) & ~63, and a code shifted to bits 2..5 selects the entry: one LOP3 builds the address, one
- * LDS returns +-((step * (2 mag + 1)) >> (bits - 1)) (src/aad_decoder.c:284-296) -- no multiply, shift, sign
- * test or negate per sample.  Rows hold 16 entries for every bit depth (entry e = code e mod 2^bits), so
- * the bits above a narrower code need no masking.  The 8 deltas sit in 8 different banks: lanes either
- * read the same word (broadcast) or different banks, never a conflict. */
-#if AAD_DEC_QTAB == 2
-/* rows per HALF step (index >> 3; (index + 8) >> 4 == ((index >> 3) + 1) >> 1): the chain keeps 8 * index and the
- * row address needs no rounding add */
-constexpr int kDecRows = 511;
-constexpr int kDecIdxScale = 8;
-#else
+ * The row of src/aad_tables.h:41 ((index + 8) >> 4) starts at byte 4 * (index + 8) & ~63 of q, and a code
+ * shifted to bits 2..5 selects the entry: one multiply-add, one LOP3 and one LDS return
+ * +-((step * (2 mag + 1)) >> (bits - 1)) (src/aad_decoder.c:284-296) -- no step load, multiply, shift,
+ * sign test or negate per sample.  Rows hold 16 entries for every bit depth (entry e = code e mod 2^bits),
+ * so the bits above a narrower code need no masking.  The 8 deltas sit in 8 different banks: lanes
+ * either read the same word (broadcast) or different banks, never a conflict.
+ * (Measured alternatives -- step table + arithmetic, 511 half-step rows, CTA shapes: profiles/r01_v7_decode.md.) */
 constexpr int kDecRows = 256;
-constexpr int kDecIdxScale = 1;
-#endif
 struct DecTables {
   int32_t q[kDecRows][16];
-  int32_t delta4[8];                      /* kDecIdxScale * index delta per magnitude code */
+  int32_t delta[8];                       /* index delta per magnitude code */
 };
-#else
-struct DecTables {
-  uint16_t step[kEncLutEntries + 7];      /* step[stepsize_index] */
-  int delta2[8][32];                      /* 2 * index delta per magnitude code, one column per lane */
-};
-constexpr int kDecIdxScale = 2;
-#endif
 
 template <int BITS, int C>
 struct DecGeom {
@@ -76,12 +61,11 @@ struct DecGeom {
   static constexpr int WARP_BYTES = ((IN_BYTES + 15) & ~15) + 32 * kDecOutPitch;
 };
 
-#if AAD_DEC_QTAB
 template <int BITS>
 __device__ __forceinline__ void dec_load_tables(DecTables &t)
 {
   for (int i = threadIdx.x; i < kDecRows * 16; i += blockDim.x) {
-    const int32_t step = g_step_table[AAD_DEC_QTAB == 2 ? ((i >> 4) + 1) >> 1 : i >> 4];
+    const int32_t step = g_step_table[i >> 4];
     const int code = i & ((1 << BITS) - 1);
     const int mag = code & ((1 << (BITS - 1)) - 1);
     const int32_t qa = (step * (2 * mag + 1)) >> (BITS - 1);
@@ -93,61 +77,39 @@ __device__ __forceinline__ void dec_load_tables(DecTables &t)
     if (BITS == 4) d = g_delta4[k];
     if (BITS == 3) d = g_delta3[k & 3];
     if (BITS == 2) d = g_delta2[k & 1];
-    t.delta4[k] = kDecIdxScale * d;
+    t.delta[k] = d;
   }
   __syncthreads();
 }
-#else
-template <int BITS>
-__device__ __forceinline__ void dec_load_tables(DecTables &t)
-{
-  for (int i = threadIdx.x; i < kEncLutEntries; i += blockDim.x) t.step[i] = g_step_table[(i + 8) >> 4];
-  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
-    const int k = i >> 5;
-    int d = 0;
-    if (BITS == 4) d = g_delta4[k];
-    if (BITS == 3) d = g_delta3[k & 3];
-    if (BITS == 2) d = g_delta2[k & 1];
-    t.delta2[k][i & 31] = 2 * d;
-  }
-  __syncthreads();
-}
-
-#endif
 
 struct DecChain {
   int32_t h0, h1, h2, h3;
   int32_t w0, w1, w2, w3;
-  int32_t idx2;   /* kDecIdxScale * stepsize_index */
+  int32_t idx;    /* stepsize_index */
   uint32_t four;  /* 4, opaque to the compiler (g_dec_four) */
 };
 
 __constant__ uint32_t g_dec_four = 4u;
 
-#if AAD_DEC_QTAB
 /* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
 template <int BITS, int POS>
-__device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t, const int *)
+__device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t)
 {
   constexpr uint32_t kMagField = ((1u << (BITS - 1)) - 1u) << 2;
   const uint32_t x = (POS >= 2) ? (v >> (POS >= 2 ? POS - 2 : 0)) : (v << (POS >= 2 ? 0 : 2 - POS));   /* code at bits 2.. */
-#if AAD_DEC_QTAB == 2
-  const uint32_t row = (uint32_t)c.idx2;
-#else
   /* 4 * (index + 8) on the multiply pipe (the ALU pipe is the one this kernel saturates): the factor comes from
    * constant memory, so ptxas cannot turn the multiply-add into an ALU-pipe LEA */
   uint32_t row;
-  asm("mad.lo.u32 %0, %1, %2, 32;" : "=r"(row) : "r"(c.idx2), "r"(c.four));
-#endif
+  asm("mad.lo.u32 %0, %1, %2, 32;" : "=r"(row) : "r"(c.idx), "r"(c.four));
   uint32_t qoff;   /* (row & ~0x3C) | (x & 0x3C); bits 0-1 of row are zero */
   asm("lop3.b32 %0, %1, %2, 0x3C, 0xD8;" : "=r"(qoff) : "r"(row), "r"(x));
   const int32_t q = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.q) + qoff);
-  const int32_t d = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.delta4) + (x & kMagField));
+  const int32_t d = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.delta) + (x & kMagField));
   const uint32_t acc = (1u << 14) + (uint32_t)c.h0 * (uint32_t)c.w0 + (uint32_t)c.h1 * (uint32_t)c.w1 +
                        (uint32_t)c.h2 * (uint32_t)c.w2 + (uint32_t)c.h3 * (uint32_t)c.w3;
   const int32_t p = (int32_t)acc >> 15;
   const int32_t r = max(__viaddmin_s32(q, p, 32767), -32768);
-  c.idx2 = __viaddmin_s32_relu(c.idx2, d, kDecIdxScale * AADF_INDEX_MAX);
+  c.idx = __viaddmin_s32_relu(c.idx, d, AADF_INDEX_MAX);
   c.w0 += (int32_t)((uint32_t)q * (uint32_t)c.h0 + (1u << 14)) >> 18;
   c.w1 += (int32_t)((uint32_t)q * (uint32_t)c.h1 + (1u << 14)) >> 18;
   c.w2 += (int32_t)((uint32_t)q * (uint32_t)c.h2 + (1u << 14)) >> 18;
@@ -158,65 +120,35 @@ __device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const Dec
   c.h0 = r;
   return r;
 }
-#else
-/* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
-template <int BITS, int POS>
-__device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t, const int *dl)
-{
-  constexpr uint32_t kMag2Mask = (1u << BITS) - 2u;          /* 2 * magnitude */
-  const int32_t step = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(t.step) + c.idx2);
-  uint32_t u = ((POS >= 1) ? (v >> (POS >= 1 ? POS - 1 : 0)) : (v << 1)) & kMag2Mask;
-  /* keep u opaque: the delta-table offset below is then one multiply-add (u * 64 + base) on the FMA pipe
-   * instead of a second shift + mask of v on the ALU pipe, which is the one this kernel saturates */
-  asm("" : "+r"(u));
-  const bool neg = (v & (1u << (POS + BITS - 1))) != 0u;
-  const int32_t qa = (int32_t)(step * u + step) >> (BITS - 1);   /* step * (2*mag + 1) */
-  const int32_t q = neg ? -qa : qa;
-  const uint32_t acc = (1u << 14) + (uint32_t)c.h0 * (uint32_t)c.w0 + (uint32_t)c.h1 * (uint32_t)c.w1 +
-                       (uint32_t)c.h2 * (uint32_t)c.w2 + (uint32_t)c.h3 * (uint32_t)c.w3;
-  const int32_t p = (int32_t)acc >> 15;
-  const int32_t r = max(__viaddmin_s32(q, p, 32767), -32768);
-  c.idx2 = __viaddmin_s32_relu(c.idx2, dl[u * 16], 2 * AADF_INDEX_MAX);   /* dl[mag * 32] */
-  c.w0 += (int32_t)((uint32_t)q * (uint32_t)c.h0 + (1u << 14)) >> 18;
-  c.w1 += (int32_t)((uint32_t)q * (uint32_t)c.h1 + (1u << 14)) >> 18;
-  c.w2 += (int32_t)((uint32_t)q * (uint32_t)c.h2 + (1u << 14)) >> 18;
-  c.w3 += (int32_t)((uint32_t)q * (uint32_t)c.h3 + (1u << 14)) >> 18;
-  c.h3 = c.h2;
-  c.h2 = c.h1;
-  c.h1 = c.h0;
-  c.h0 = r;
-  return r;
-}
-#endif
 
 __device__ __forceinline__ uint32_t dec_pack2(int32_t a, int32_t b) { return __byte_perm((uint32_t)a, (uint32_t)b, 0x5410); }
 
 /* All codes of one byte (4-bit: 2, 2-bit: 4), byte at bits [8*K, 8*K+8) of v; samples appended to o[]. */
 template <int BITS, int K>
-__device__ __forceinline__ void dec_byte(DecChain &c, uint32_t v, const DecTables &t, const int *dl, int32_t *o)
+__device__ __forceinline__ void dec_byte(DecChain &c, uint32_t v, const DecTables &t, int32_t *o)
 {
   if (BITS == 4) {
-    o[0] = dec_sample<4, 8 * K + 4>(c, v, t, dl);
-    o[1] = dec_sample<4, 8 * K>(c, v, t, dl);
+    o[0] = dec_sample<4, 8 * K + 4>(c, v, t);
+    o[1] = dec_sample<4, 8 * K>(c, v, t);
   } else {
-    o[0] = dec_sample<2, 8 * K + 6>(c, v, t, dl);
-    o[1] = dec_sample<2, 8 * K + 4>(c, v, t, dl);
-    o[2] = dec_sample<2, 8 * K + 2>(c, v, t, dl);
-    o[3] = dec_sample<2, 8 * K>(c, v, t, dl);
+    o[0] = dec_sample<2, 8 * K + 6>(c, v, t);
+    o[1] = dec_sample<2, 8 * K + 4>(c, v, t);
+    o[2] = dec_sample<2, 8 * K + 2>(c, v, t);
+    o[3] = dec_sample<2, 8 * K>(c, v, t);
   }
 }
 
 /* the 8 codes of one 3-bit group held big-endian in the low 24 bits of g */
-__device__ __forceinline__ void dec_group3(DecChain &c, uint32_t g, const DecTables &t, const int *dl, int32_t *o)
+__device__ __forceinline__ void dec_group3(DecChain &c, uint32_t g, const DecTables &t, int32_t *o)
 {
-  o[0] = dec_sample<3, 21>(c, g, t, dl);
-  o[1] = dec_sample<3, 18>(c, g, t, dl);
-  o[2] = dec_sample<3, 15>(c, g, t, dl);
-  o[3] = dec_sample<3, 12>(c, g, t, dl);
-  o[4] = dec_sample<3, 9>(c, g, t, dl);
-  o[5] = dec_sample<3, 6>(c, g, t, dl);
-  o[6] = dec_sample<3, 3>(c, g, t, dl);
-  o[7] = dec_sample<3, 0>(c, g, t, dl);
+  o[0] = dec_sample<3, 21>(c, g, t);
+  o[1] = dec_sample<3, 18>(c, g, t);
+  o[2] = dec_sample<3, 15>(c, g, t);
+  o[3] = dec_sample<3, 12>(c, g, t);
+  o[4] = dec_sample<3, 9>(c, g, t);
+  o[5] = dec_sample<3, 6>(c, g, t);
+  o[6] = dec_sample<3, 3>(c, g, t);
+  o[7] = dec_sample<3, 0>(c, g, t);
 }
 
 /* store N (multiple of 4) samples to the lane's shared output row at sample offset `at` */
@@ -240,11 +172,6 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
   const uint32_t warp = threadIdx.x >> 5;
   unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * G::WARP_BYTES;
   unsigned char *out_rows = in_rows + ((G::IN_BYTES + 15) & ~15);
-#if AAD_DEC_QTAB
-  const int *dl = nullptr;
-#else
-  const int *dl = &tab.delta2[0][lane];
-#endif
 
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
@@ -307,7 +234,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     auto in_u8 = [&](uint32_t pos) -> uint32_t { return irow[a_r + pos]; };
 
     DecChain c;
-    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx = 0;
     c.four = g_dec_four;
 
     const uint32_t windows = (bs + G::TB - 1) / G::TB;
@@ -336,8 +263,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         /* block header, src/aad_decoder.c:364-380: u16 (index << 4 | shift), 4 x (u16 weight, u16 history) */
         const uint32_t hp = AADF_CHANNEL_HEADER_BYTES * ch;
         const uint32_t head = (in_u8(hp) << 8) | in_u8(hp + 1);
-        c.idx2 = kDecIdxScale * (int32_t)(int16_t)(head >> 4);
-        c.idx2 = max(0, min(c.idx2, kDecIdxScale * AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
+        c.idx = (int32_t)(int16_t)(head >> 4);
+        c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */    /* a corrupt header must not index outside the table */
         const uint32_t shift = head & 0xFu;
         int32_t wv[4], hv[4];
   #pragma unroll
@@ -355,15 +282,15 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
           /* half a step: the 18-byte header leaves the row 2 bytes off word alignment */
           if (BITS == 3) {
             int32_t o[16];
-            dec_group3(c, (in_u8(pos) << 16) | (in_u8(pos + 1) << 8) | in_u8(pos + 2), tab, dl, o);
-            dec_group3(c, (in_u8(pos + 3) << 16) | (in_u8(pos + 4) << 8) | in_u8(pos + 5), tab, dl, o + 8);
+            dec_group3(c, (in_u8(pos) << 16) | (in_u8(pos + 1) << 8) | in_u8(pos + 2), tab, o);
+            dec_group3(c, (in_u8(pos + 3) << 16) | (in_u8(pos + 4) << 8) | in_u8(pos + 5), tab, o + 8);
             dec_emit<16>(orow, produced, o);
             produced += 16;
           } else {
             const uint32_t v = in_u8(pos) | (in_u8(pos + 1) << 8);
             int32_t o[2 * (BITS == 4 ? 2 : 4)];
-            dec_byte<BITS, 0>(c, v, tab, dl, o);
-            dec_byte<BITS, 1>(c, v, tab, dl, o + (BITS == 4 ? 2 : 4));
+            dec_byte<BITS, 0>(c, v, tab, o);
+            dec_byte<BITS, 1>(c, v, tab, o + (BITS == 4 ? 2 : 4));
             dec_emit<2 * (BITS == 4 ? 2 : 4)>(orow, produced, o);
             produced += 2 * (BITS == 4 ? 2 : 4);
           }
@@ -389,14 +316,14 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
             }
             int32_t o[G::SPS];
             if (C == 1) {
-              dec_group3(c, __byte_perm(x[0], 0u, 0x4012), tab, dl, o);
-              dec_group3(c, __byte_perm(x[0], x[1], 0x4345), tab, dl, o + 8);
-              dec_group3(c, __byte_perm(x[1], x[2], 0x4234), tab, dl, o + 16);
-              dec_group3(c, __byte_perm(x[2], 0u, 0x4123), tab, dl, o + 24);
+              dec_group3(c, __byte_perm(x[0], 0u, 0x4012), tab, o);
+              dec_group3(c, __byte_perm(x[0], x[1], 0x4345), tab, o + 8);
+              dec_group3(c, __byte_perm(x[1], x[2], 0x4234), tab, o + 16);
+              dec_group3(c, __byte_perm(x[2], 0u, 0x4123), tab, o + 24);
             } else {   /* two channels: groups alternate, 3 bytes each */
               const uint32_t sel_a = ch ? 0x0345u : 0x0012u, sel_b = ch ? 0x0567u : 0x0234u;
-              dec_group3(c, __byte_perm(x[0], x[1], sel_a), tab, dl, o);
-              dec_group3(c, __byte_perm(x[1], x[2], sel_b), tab, dl, o + 8);
+              dec_group3(c, __byte_perm(x[0], x[1], sel_a), tab, o);
+              dec_group3(c, __byte_perm(x[1], x[2], sel_b), tab, o + 8);
             }
             dec_emit<G::SPS>(orow, produced, o);
           } else {
@@ -406,14 +333,14 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
             constexpr int PER_BYTE = (BITS == 4) ? 2 : 4;
             int32_t o[G::SPS];
             if (C == 1) {
-              dec_byte<BITS, 0>(c, v, tab, dl, o);
-              dec_byte<BITS, 1>(c, v, tab, dl, o + PER_BYTE);
-              dec_byte<BITS, 2>(c, v, tab, dl, o + 2 * PER_BYTE);
-              dec_byte<BITS, 3>(c, v, tab, dl, o + 3 * PER_BYTE);
+              dec_byte<BITS, 0>(c, v, tab, o);
+              dec_byte<BITS, 1>(c, v, tab, o + PER_BYTE);
+              dec_byte<BITS, 2>(c, v, tab, o + 2 * PER_BYTE);
+              dec_byte<BITS, 3>(c, v, tab, o + 3 * PER_BYTE);
             } else {   /* two channels: bytes alternate */
               v >>= 8u * ch;
-              dec_byte<BITS, 0>(c, v, tab, dl, o);
-              dec_byte<BITS, 2>(c, v, tab, dl, o + PER_BYTE);
+              dec_byte<BITS, 0>(c, v, tab, o);
+              dec_byte<BITS, 2>(c, v, tab, o + PER_BYTE);
             }
             dec_emit<G::SPS>(orow, produced, o);
           }
@@ -489,11 +416,6 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
   const uint32_t warp = threadIdx.x >> 5;
   unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * (in_bytes + 32u * kDecOutPitch);
   unsigned char *out_rows = in_rows + in_bytes;
-#if AAD_DEC_QTAB
-  const int *dl = nullptr;
-#else
-  const int *dl = &tab.delta2[0][lane];
-#endif
 
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
@@ -557,7 +479,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     unsigned char *orow = out_rows + lane * kDecOutPitch;
 
     DecChain c;
-    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx2 = 0;
+    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx = 0;
     c.four = g_dec_four;
 
     const uint32_t windows = (bs + TB - 1) / TB;
@@ -585,8 +507,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
       if (w == 0) {   /* block header, src/aad_decoder.c:364-391 */
         const unsigned char *hp = irow + AADF_CHANNEL_HEADER_BYTES * ch;
         const uint32_t head = ((uint32_t)hp[0] << 8) | hp[1];
-        c.idx2 = kDecIdxScale * (int32_t)(int16_t)(head >> 4);
-        c.idx2 = max(0, min(c.idx2, kDecIdxScale * AADF_INDEX_MAX));
+        c.idx = (int32_t)(int16_t)(head >> 4);
+        c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
         const uint32_t shift = head & 0xFu;
         int32_t wv[4], hv[4];
   #pragma unroll
@@ -613,8 +535,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
             const uint32_t v = (uint32_t)bp[0] | ((uint32_t)bp[gstride] << 8);
             bp += 2u * gstride;
             int32_t o[4];
-            dec_byte<4, 0>(c, v, tab, dl, o);
-            dec_byte<4, 1>(c, v, tab, dl, o + 2);
+            dec_byte<4, 0>(c, v, tab, o);
+            dec_byte<4, 1>(c, v, tab, o + 2);
             dec_emit<4>(orow, produced, o);
             produced += 4;
           }
@@ -624,7 +546,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
             const uint32_t v = ((uint32_t)bp[0] << 16) | ((uint32_t)bp[1] << 8) | bp[2];
             bp += gstride;
             int32_t o[8];
-            dec_group3(c, v, tab, dl, o);
+            dec_group3(c, v, tab, o);
             dec_emit<8>(orow, produced, o);
             produced += 8;
           }
@@ -634,7 +556,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
             const uint32_t v = bp[0];
             bp += gstride;
             int32_t o[4];
-            dec_byte<2, 0>(c, v, tab, dl, o);
+            dec_byte<2, 0>(c, v, tab, o);
             dec_emit<4>(orow, produced, o);
             produced += 4;
           }
