@@ -160,6 +160,47 @@ __device__ __forceinline__ void dec_emit(unsigned char *orow, uint32_t at, const
     *reinterpret_cast<uint2 *>(orow + 2 * (at + k)) = make_uint2(dec_pack2(o[k], o[k + 1]), dec_pack2(o[k + 2], o[k + 3]));
 }
 
+/* 16 bytes at q (16-byte aligned) for the shared input rows; bytes at or past `end` -- the end of the stream's
+ * valid data -- read as zero, a null q (a loader lane without a chunk) as well */
+__device__ __forceinline__ uint4 dec_fetch16(const uint8_t *q, const uint8_t *end)
+{
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (q == nullptr || q >= end) return v;
+  if (q + 16 <= end) return __ldg(reinterpret_cast<const uint4 *>(q));
+  unsigned char tmp[16];                      /* the chunk that straddles the end of the data */
+#pragma unroll
+  for (int k = 0; k < 16; k++) tmp[k] = (q + k < end) ? q[k] : (unsigned char)0;
+  v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
+  v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
+  v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
+  v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+  return v;
+}
+
+/* Flush of a window when the chains of the warp do not all deliver a whole block (a stream's last blocks,
+ * short output buffers, missing data): row rr of the shared output rows holds `produced` samples of the chain
+ * in lane rr, of which those below that chain's n_row go to its global row, as one coalesced run of 8-byte
+ * pieces plus a scalar tail. */
+__device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, uint32_t rows, uint32_t n_row,
+                                                 uint32_t produced, int16_t *grow, uint32_t out_base, uint32_t lane)
+{
+  for (uint32_t rr = 0; rr < rows; rr++) {
+    const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+    const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+    const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+    if (n_rr <= out_base) continue;                       /* uniform */
+    const uint32_t count = min(made, n_rr - out_base);
+    int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+    const unsigned char *srow = out_rows + rr * kDecOutPitch;
+    const uint32_t s0 = lane * 4u;
+    if (s0 + 4u <= count) {
+      *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+    } else {
+      for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+    }
+  }
+}
+
 template <int BITS, int C>
 __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_decode_params p)
 {
@@ -203,7 +244,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
     const uint8_t *ld_ptr[G::IN_LOADS];
     uint32_t ld_smem[G::IN_LOADS];
-  #pragma unroll
+#pragma unroll
     for (int m = 0; m < G::IN_LOADS; m++) {
       const uint32_t f = lane + 32u * m;
       const uint32_t rr = f / G::IN_CHUNKS, cc = f % G::IN_CHUNKS;
@@ -212,20 +253,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       ld_smem[m] = rr * G::IN_PITCH + 16u * cc;
     }
     const uint8_t *slot_end = slot + size;
-    auto fetch = [&](int m) -> uint4 {
-      const uint8_t *q = ld_ptr[m];
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (q == nullptr || q >= slot_end) return v;
-      if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
-      unsigned char tmp[16];                      /* the chunk that straddles the end of the data: */
-  #pragma unroll
-      for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past it read as zero */
-      v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
-      v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
-      v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
-      v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
-      return v;
-    };
+    auto fetch = [&](int m) -> uint4 { return dec_fetch16(ld_ptr[m], slot_end); };
 
     /* reader role: this lane's block row in shared memory */
     const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
@@ -239,18 +267,18 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
 
     const uint32_t windows = (bs + G::TB - 1) / G::TB;
     uint4 pre[G::IN_LOADS];
-  #pragma unroll
+#pragma unroll
     for (int m = 0; m < G::IN_LOADS; m++) pre[m] = fetch(m);
 
     uint32_t out_base = 0;                                   /* first output sample of this window */
     for (uint32_t w = 0; w < windows; w++) {
       /* stage this window, start the next one */
-  #pragma unroll
+#pragma unroll
       for (int m = 0; m < G::IN_LOADS; m++)
         if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
       __syncwarp();
       if (w + 1 < windows) {
-  #pragma unroll
+#pragma unroll
         for (int m = 0; m < G::IN_LOADS; m++) {
           if (ld_ptr[m] != nullptr) ld_ptr[m] += G::TB;
           pre[m] = fetch(m);
@@ -267,7 +295,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */    /* a corrupt header must not index outside the table */
         const uint32_t shift = head & 0xFu;
         int32_t wv[4], hv[4];
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < 4; k++) {
           wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)((in_u8(hp + 2 + 4 * k) << 8) | in_u8(hp + 3 + 4 * k)) << shift);
           hv[k] = (int32_t)(int16_t)((in_u8(hp + 4 + 4 * k) << 8) | in_u8(hp + 5 + 4 * k));
@@ -308,7 +336,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         for (uint32_t s = 0; s < steps; s++) {
           if (BITS == 3) {
             uint32_t x[3];
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < 3; k++) {
               const uint32_t hi = *wp++;
               x[k] = __funnelshift_r(lo, hi, sh);
@@ -357,27 +385,13 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         if (lane * 4u + 4u <= min(produced, spb - out_base)) {
           const unsigned char *srow = out_rows + 8u * lane;
           int16_t *dst = grow0 + out_base + 4u * lane;
-  #pragma unroll
+#pragma unroll
           for (uint32_t rr = 0; rr < 32; rr++)
             *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
                 *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
         }
       } else {
-        for (uint32_t rr = 0; rr < 32; rr++) {
-          const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
-          const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
-          const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
-          if (n_rr <= out_base) continue;                       /* uniform */
-          const uint32_t count = min(made, n_rr - out_base);
-          int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
-          const unsigned char *srow = out_rows + rr * kDecOutPitch;
-          const uint32_t s0 = lane * 4u;
-          if (s0 + 4u <= count) {
-            *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
-          } else {
-            for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
-          }
-        }
+        dec_flush_ragged(out_rows, 32u, n_row, produced, grow, out_base, lane);
       }
       out_base += produced;       /* identical in every lane */
       __syncwarp();
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
     const uint8_t *ld_ptr[kLoads];
     uint32_t ld_smem[kLoads];
-  #pragma unroll
+#pragma unroll
     for (int m = 0; m < kLoads; m++) {
       const uint32_t f = lane + 32u * m;
       const uint32_t rr = f / chunks, cc = f % chunks;
@@ -458,20 +472,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
       ld_smem[m] = rr * pitch + 16u * cc;
     }
     const uint8_t *slot_end = slot + size;
-    auto fetch = [&](int m) -> uint4 {
-      const uint8_t *q = ld_ptr[m];
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (q == nullptr || q >= slot_end) return v;
-      if (q + 16 <= slot_end) return __ldg(reinterpret_cast<const uint4 *>(q));
-      unsigned char tmp[16];
-  #pragma unroll
-      for (int k = 0; k < 16; k++) tmp[k] = (q + k < slot_end) ? q[k] : (unsigned char)0;   /* bytes past the data read as zero */
-      v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
-      v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
-      v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
-      v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
-      return v;
-    };
+    auto fetch = [&](int m) -> uint4 { return dec_fetch16(ld_ptr[m], slot_end); };
 
     /* reader role */
     const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
@@ -485,17 +486,17 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     const uint32_t windows = (bs + TB - 1) / TB;
     const uint32_t gstride = GB * C;
     uint4 pre[kLoads];
-  #pragma unroll
+#pragma unroll
     for (int m = 0; m < kLoads; m++) pre[m] = fetch(m);
 
     uint32_t out_base = 0;
     for (uint32_t w = 0; w < windows; w++) {
-  #pragma unroll
+#pragma unroll
       for (int m = 0; m < kLoads; m++)
         if (ld_ptr[m] != nullptr) *reinterpret_cast<uint4 *>(in_rows + ld_smem[m]) = pre[m];
       __syncwarp();
       if (w + 1 < windows) {
-  #pragma unroll
+#pragma unroll
         for (int m = 0; m < kLoads; m++) {
           if (ld_ptr[m] != nullptr) ld_ptr[m] += TB;
           pre[m] = fetch(m);
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
         c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
         const uint32_t shift = head & 0xFu;
         int32_t wv[4], hv[4];
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < 4; k++) {
           wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)(((uint32_t)hp[2 + 4 * k] << 8) | hp[3 + 4 * k]) << shift);
           hv[k] = (int32_t)(int16_t)(((uint32_t)hp[4 + 4 * k] << 8) | hp[5 + 4 * k]);
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
         const unsigned char *bp = irow + pos + GB * ch;
         const uint32_t groups = (TB - pos) / gstride;          /* even for 4-bit in every window */
         if (BITS == 4) {
-  #pragma unroll 2
+#pragma unroll 2
           for (uint32_t g = 0; g < groups; g += 2) {
             const uint32_t v = (uint32_t)bp[0] | ((uint32_t)bp[gstride] << 8);
             bp += 2u * gstride;
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
             produced += 4;
           }
         } else if (BITS == 3) {
-  #pragma unroll 2
+#pragma unroll 2
           for (uint32_t g = 0; g < groups; g++) {
             const uint32_t v = ((uint32_t)bp[0] << 16) | ((uint32_t)bp[1] << 8) | bp[2];
             bp += gstride;
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
             produced += 8;
           }
         } else {
-  #pragma unroll 2
+#pragma unroll 2
           for (uint32_t g = 0; g < groups; g++) {
             const uint32_t v = bp[0];
             bp += gstride;
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
           int16_t *dst_blk = grow0 + out_base + 4u * lane;
           int16_t *dst = dst_blk;
           uint32_t rch = 0;
-  #pragma unroll 4
+#pragma unroll 4
           for (uint32_t rr = 0; rr < active; rr++) {
             *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
             dst += p.pcm_ch_stride;
@@ -579,21 +580,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
           }
         }
       } else {
-        for (uint32_t rr = 0; rr < active; rr++) {
-          const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
-          const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
-          const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
-          if (n_rr <= out_base) continue;                       /* uniform */
-          const uint32_t count = min(made, n_rr - out_base);
-          int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
-          const unsigned char *srow = out_rows + rr * kDecOutPitch;
-          const uint32_t s0 = lane * 4u;
-          if (s0 + 4u <= count) {
-            *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
-          } else {
-            for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
-          }
-        }
+        dec_flush_ragged(out_rows, active, n_row, produced, grow, out_base, lane);
       }
       out_base += produced;       /* identical in every lane */
       __syncwarp();
