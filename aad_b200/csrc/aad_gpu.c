@@ -72,6 +72,7 @@ struct AADGpu *AADGpu_Create(int device)
   struct AADGpu *g = (struct AADGpu *)calloc(1, sizeof(*g));
   if (!g) return NULL;
   g->device = device;
+  pthread_mutex_init(&g->lock, NULL);
   cudaError_t e = cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking);
@@ -102,6 +103,7 @@ void AADGpu_Destroy(struct AADGpu *g)
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_run) cudaStreamDestroy(g->s_run);
   if (g->s_out) cudaStreamDestroy(g->s_out);
+  pthread_mutex_destroy(&g->lock);
   free(g);
 }
 
@@ -325,7 +327,7 @@ void AADGpu_SynthLut(int16_t lut[1024])
   for (int k = 0; k < 1024; k++) lut[k] = (int16_t)lrint(32767.0 * sin(2.0 * 3.14159265358979323846 * k / 1024.0));
 }
 
-AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch, uint32_t first_stream,
+static AADApiResult AADGpu_SynthBatchDevice_unlocked(struct AADGpu *gpu, const struct AADGpuBatch *batch, uint32_t first_stream,
                                      int16_t *pcm_dev, void *stream)
 {
   if (!gpu || !batch || !pcm_dev) return AAD_APIRESULT_INVALID_ARGUMENT;
@@ -351,6 +353,16 @@ AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatc
   p.lut = (const int16_t *)gpu->lut.ptr;
   CU((cudaError_t)aadk_launch_synth(&p, stream), "synth kernel launch");
   return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch, uint32_t first_stream,
+                                     int16_t *pcm_dev, void *stream)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_SynthBatchDevice_unlocked(gpu, batch, first_stream, pcm_dev, stream);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
 }
 
 AADApiResult AADGpu_Deinterleave16Device(struct AADGpu *gpu, const int16_t *interleaved_dev, int16_t *planar_dev,
@@ -420,7 +432,7 @@ static cudaError_t copy_pcm_slice(const struct AADGpuBatch *b, uint32_t C, int t
   return cudaSuccess;
 }
 
-AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
+static AADApiResult AADGpu_EncodeBatch_unlocked(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
                                 const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes)
 {
   if (!gpu || !batch || !pcm || !aad) return AAD_APIRESULT_INVALID_ARGUMENT;
@@ -493,7 +505,17 @@ AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
   return AAD_APIRESULT_OK;
 }
 
-AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad,
+AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
+                                const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_EncodeBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
+static AADApiResult AADGpu_DecodeBatch_unlocked(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad,
                                 const uint32_t *sizes, int16_t *pcm)
 {
   if (!gpu || !batch || !pcm || !aad) return AAD_APIRESULT_INVALID_ARGUMENT;
@@ -565,12 +587,22 @@ AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
   return AAD_APIRESULT_OK;
 }
 
+AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad,
+                                const uint32_t *sizes, int16_t *pcm)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_DecodeBatch_unlocked(gpu, batch, aad, sizes, pcm);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
 /* Encode a batch and decode it back in one pass over the data (what src/main.c:275-346 does for one
  * file, execute_reconstruction_core): per block-range slice  H2D pcm | encode | decode | D2H .aad + D2H pcm.
  * The encoded streams never make the round trip over PCIe, and the two directions of the link are busy
  * at the same time: ~25 GB per 12,500 ten-second clips instead of 27.7 GB half-duplex.  aad / out_sizes
  * may be NULL when only the reconstruction is wanted. */
-AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
+static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
                                      const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes,
                                      int16_t *reconstructed)
 {
@@ -663,9 +695,20 @@ AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatc
   return AAD_APIRESULT_OK;
 }
 
+AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
+                                     const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes,
+                                     int16_t *reconstructed)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_ReconstructBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes, reconstructed);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
 /* ---- single-stream paths behind the drop-in API ------------------------------------------- */
 
-AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, uint32_t sampling_rate,
+static AADApiResult aadgpu_encode_stream_i32_unlocked(struct AADGpu *gpu, const struct aadf_geometry *geo, uint32_t sampling_rate,
                                       uint32_t trials, const int32_t *const *input, uint32_t num_samples,
                                       int32_t *state, uint8_t *data, uint32_t *output_size)
 {
@@ -711,7 +754,18 @@ AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
   return AAD_APIRESULT_OK;
 }
 
-AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *data,
+AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, uint32_t sampling_rate,
+                                      uint32_t trials, const int32_t *const *input, uint32_t num_samples,
+                                      int32_t *state, uint8_t *data, uint32_t *output_size)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = aadgpu_encode_stream_i32_unlocked(gpu, geo, sampling_rate, trials, input, num_samples, state, data, output_size);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
+static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *data,
                                       uint32_t data_size, uint32_t num_blocks, uint32_t num_samples,
                                       uint32_t buf_samples, int32_t *const *buffer)
 {
@@ -770,6 +824,17 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
   return AAD_APIRESULT_OK;
 }
 
+AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *data,
+                                      uint32_t data_size, uint32_t num_blocks, uint32_t num_samples,
+                                      uint32_t buf_samples, int32_t *const *buffer)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = aadgpu_decode_stream_i32_unlocked(gpu, geo, data, data_size, num_blocks, num_samples, buf_samples, buffer);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
 /* ---- WAV-order (interleaved int16) single-stream paths: what `aad -e / -d / -r` do ---------- */
 
 /* src/main.c:175-179 + AADEncoder_EncodeWhole, with the de-interleave done on the device: the
@@ -813,7 +878,7 @@ static AADApiResult encode_interleaved_device(struct AADGpu *gpu, const struct A
   return AAD_APIRESULT_OK;
 }
 
-AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+static AADApiResult AADGpu_EncodeInterleaved16_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
                                         const int16_t *interleaved, uint32_t num_samples, uint8_t *data,
                                         uint32_t data_size, uint32_t *output_size)
 {
@@ -832,6 +897,17 @@ AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEnco
   CU(cudaStreamSynchronize(gpu->s_run), "sync");
   *output_size = (uint32_t)bytes;
   return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                        const int16_t *interleaved, uint32_t num_samples, uint8_t *data,
+                                        uint32_t data_size, uint32_t *output_size)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_EncodeInterleaved16_unlocked(gpu, prm, interleaved, num_samples, data, data_size, output_size);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
 }
 
 /* decode the stream at d_aad (device) into gpu->pcm (planar) and gpu->wav (interleaved) */
@@ -878,7 +954,7 @@ static AADApiResult parse_stream_header(const uint8_t *data, uint32_t data_size,
   return aaddec_check_header(h);
 }
 
-AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
+static AADApiResult AADGpu_DecodeInterleaved16_unlocked(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
                                         int16_t *interleaved, uint32_t capacity_samples)
 {
   if (!gpu || !data || !interleaved) return AAD_APIRESULT_INVALID_ARGUMENT;
@@ -900,9 +976,19 @@ AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data,
   return AAD_APIRESULT_OK;
 }
 
+AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
+                                        int16_t *interleaved, uint32_t capacity_samples)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_DecodeInterleaved16_unlocked(gpu, data, data_size, interleaved, capacity_samples);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
 /* src/main.c:275-346 (execute_reconstruction_core): encode, then decode what was encoded; the
  * stream never leaves the device. */
-AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+static AADApiResult AADGpu_ReconstructInterleaved16_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
                                              const int16_t *interleaved, uint32_t num_samples,
                                              int16_t *reconstructed, uint32_t *encoded_size)
 {
@@ -932,6 +1018,17 @@ AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AA
   return AAD_APIRESULT_OK;
 }
 
+AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                             const int16_t *interleaved, uint32_t num_samples,
+                                             int16_t *reconstructed, uint32_t *encoded_size)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_ReconstructInterleaved16_unlocked(gpu, prm, interleaved, num_samples, reconstructed, encoded_size);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
 /* ---- the analysis modes of the command line, src/main.c:275-503, with the samples staying on the device -------- */
 
 static void header_of(const struct AADEncodeParameter *prm, const struct aadf_geometry *geo, uint32_t num_samples,
@@ -947,7 +1044,7 @@ static void header_of(const struct AADEncodeParameter *prm, const struct aadf_ge
   h->ch_process_method = prm->ch_process_method;
 }
 
-AADApiResult AADGpu_AnalyzeWav(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
+static AADApiResult AADGpu_AnalyzeWav_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
                                uint32_t wav_bits_per_sample, uint32_t num_samples, enum AADGpuAnalysis what,
                                uint8_t *out_data, double stats[3], uint32_t *encoded_size)
 {
@@ -1003,6 +1100,17 @@ AADApiResult AADGpu_AnalyzeWav(struct AADGpu *gpu, const struct AADEncodeParamet
   }
   if (encoded_size) *encoded_size = (uint32_t)bytes;
   return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_AnalyzeWav(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
+                               uint32_t wav_bits_per_sample, uint32_t num_samples, enum AADGpuAnalysis what,
+                               uint8_t *out_data, double stats[3], uint32_t *encoded_size)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_AnalyzeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, what, out_data, stats, encoded_size);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
 }
 
 /* ---- several devices of one box: shard, run one host thread per device, done ---------------- */
@@ -1185,7 +1293,7 @@ AADApiResult AADGpuGroup_DecodeBatch(struct AADGpuGroup *g, const struct AADGpuB
 }
 
 /* blocks [b0, b1) of one stream -> interleaved samples [b0*spb, min(b1*spb, ns)) of the caller's buffer */
-static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
+static AADApiResult decode_stream_range_unlocked(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
                                         uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved)
 {
   const uint32_t C = h->num_channels, spb = h->num_samples_per_block, bs = h->block_size, ns = h->num_samples;
@@ -1233,6 +1341,16 @@ static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHead
   return AAD_APIRESULT_OK;
 }
 
+static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
+                                        uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = decode_stream_range_unlocked(gpu, h, data, data_size, b0, b1, interleaved);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
 AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_t *data, uint32_t data_size,
                                              int16_t *interleaved, uint32_t capacity_samples)
 {
@@ -1275,7 +1393,7 @@ AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_
 /* blocks [b0, b1) of one stream (b0 on a segment boundary) from interleaved samples [b0*spb, min(b1*spb, ns)):
  * the shard copies only its own samples, encodes its segments as independent chains and writes its own byte
  * range of the caller's stream (the 31-byte file header with block 0) */
-static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
+static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
                                         const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
                                         uint8_t *data)
 {
@@ -1327,6 +1445,17 @@ static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEnco
   CU(cudaMemcpyAsync(data + byte0 - lead, d_block0 - lead, (size_t)(span + lead), cudaMemcpyDeviceToHost, s), "D2H aad shard");
   CU(cudaStreamSynchronize(s), "sync");
   return AAD_APIRESULT_OK;
+}
+
+static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
+                                        const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
+                                        uint8_t *data)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = encode_stream_range_unlocked(gpu, prm, segment_blocks, interleaved, num_samples, b0, b1, data);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
 }
 
 AADApiResult AADGpuGroup_EncodeInterleaved16(struct AADGpuGroup *g, const struct AADEncodeParameter *prm,

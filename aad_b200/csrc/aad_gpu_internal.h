@@ -6,6 +6,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <pthread.h>
 #include <cuda_runtime_api.h>
 
 #include "aad_b200.h"
@@ -21,8 +22,13 @@ struct aadgpu_buffer {
   size_t cap;
 };
 
+/* One context = one device + its streams and grow-only scratch buffers.  Every entry point that uses the scratch
+ * holds `lock` for its duration, so a context may be shared by threads (the drop-in AADEncoder_* / AADDecoder_*
+ * handles of all threads share the process-wide default context: distinct handles stay independent, as in the
+ * reference, their GPU work is serialised). */
 struct AADGpu {
   int device;
+  pthread_mutex_t lock;
   cudaStream_t s_in, s_run, s_out;
   cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES];
   struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2, raw, stats;

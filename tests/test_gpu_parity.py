@@ -310,6 +310,51 @@ def test_handle_reuse_carries_state(product, gpu_ctx, oracle):
     assert ga == oa and gb == ob and gc == oc
 
 
+def test_dropin_handles_are_independent_across_threads(product, gpu_ctx, oracle):
+    """The reference has no shared mutable state: distinct handles may be used from distinct threads
+    at the same time.  Here every handle of the process shares the default device context, whose entry points
+    serialise on a per-context lock: 8 threads x 12 encode + decode calls of different shapes, every result against
+    the oracle.  (ctypes releases the GIL during the calls, so they do overlap.)"""
+    from concurrent.futures import ThreadPoolExecutor
+    api, gpu = product
+    rng = np.random.default_rng(77)
+    cases = []
+    for i in range(96):
+        ch = int(rng.choice([1, 2, 2, 8]))
+        cases.append(dict(pcm=aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], ch, int(rng.integers(1, 9000)), 300 + i),
+                          bits=int(rng.integers(2, 5)), ms=bool(rng.integers(2)) and ch >= 2, trials=int(rng.integers(0, 3))))
+    want = []
+    for c in cases:
+        rc, data = oracle.encode(c["pcm"], 44100, c["bits"], 1024, c["ms"], c["trials"])
+        assert rc == 0
+        want.append((data, oracle.decode(data)[1]))
+
+    def work(i):
+        c = cases[i]
+        rc, data = api.encode_whole(c["pcm"], 44100, c["bits"], 1024, c["ms"], c["trials"])
+        rc2, dec, _ = api.decode_whole(want[i][0])
+        return rc, data, rc2, dec
+
+    with ThreadPoolExecutor(8) as pool:
+        got = list(pool.map(work, range(len(cases))))
+    for i, (rc, data, rc2, dec) in enumerate(got):
+        assert rc == 0 and data == want[i][0], i
+        assert rc2 == 0 and np.array_equal(dec, want[i][1].astype(np.int32)), i
+    # explicit contexts too: one shared by all threads
+    pcm = np.stack([aadtest.signal("music", 1, 5000, s) for s in range(6)])
+
+    def batch(i):
+        aad, sizes = gpu.encode_batch(gpu_ctx, pcm[i:i + 3], 44100, 4, 1024, False, 1)
+        return [aad[k, :sizes[k]].tobytes() for k in range(3)]
+
+    with ThreadPoolExecutor(4) as pool:
+        res = list(pool.map(batch, [0, 1, 2, 3] * 4))
+    for j, r in enumerate(res):
+        i = [0, 1, 2, 3][j % 4]
+        for k in range(3):
+            assert r[k] == oracle.encode(pcm[i + k], 44100, 4, 1024, False, 1)[1], (j, k)
+
+
 def test_decode_block_and_oversized_buffer(product, gpu_ctx, oracle):
     api, _ = product
     pcm = aadtest.signal("music", 2, 3000, 7)
