@@ -51,7 +51,10 @@ struct DecGeom {
   static constexpr int GB = (BITS == 3) ? 3 : 1;
   static constexpr int TB = 16 * BITS * C;                 /* input bytes per block per window */
   static constexpr int IN_CHUNKS = TB / 16 + 1;            /* aligned superset */
-  static constexpr int IN_PITCH = 16 * IN_CHUNKS;
+  /* row pitch: an ODD number of 16-byte chunks, so the rows of a warp start in 8 different banks (4 words apart);
+   * with an even count -- 4 chunks for mono 3-bit -- 32 rows would share 2 banks and every per-lane word read of
+   * the sample loop would be a 16-way conflict */
+  static constexpr int IN_PITCH = 16 * (IN_CHUNKS | 1);
   static constexpr int IN_ROWS = 32 / C;
   static constexpr int IN_LOADS = (IN_ROWS * IN_CHUNKS + 31) / 32;
   static constexpr int IN_BYTES = IN_ROWS * IN_PITCH + 16; /* + slack for the funnel look-ahead word */
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
   const uint32_t rows = 32u / C, active = rows * C;
   const uint32_t TB = 16u * BITS * C;                  /* input bytes per block per window */
   const uint32_t chunks = BITS * C + 1u;               /* 16-byte chunks per row: aligned superset */
-  const uint32_t pitch = 16u * chunks;
+  const uint32_t pitch = 16u * (chunks | 1u);              /* odd number of chunks: rows spread over the banks (DecGeom) */
   const uint32_t in_bytes = (rows * pitch + 16u + 15u) & ~15u;
 
   const uint32_t lane = threadIdx.x & 31u;
@@ -640,7 +643,7 @@ template <int BITS>
 int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
 {
   const uint32_t C = p.geo.channels, rows = 32u / C;
-  const size_t in_bytes = ((size_t)rows * 16u * (BITS * C + 1u) + 16u + 15u) & ~(size_t)15;
+  const size_t in_bytes = ((size_t)rows * 16u * ((BITS * C + 1u) | 1u) + 16u + 15u) & ~(size_t)15;
   const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (in_bytes + 32u * kDecOutPitch);
   cudaError_t e = cudaFuncSetAttribute(aad_decode_wide<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
