@@ -335,7 +335,9 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow + (at & ~3u));
         const uint32_t sh = (at & 3u) * 8u;
         uint32_t lo = *wp++;
-        const uint32_t steps = (G::TB - pos) / G::STEP_BYTES;
+        /* the block's last window stops where the block's samples end (the same in every lane) */
+        const uint32_t left = (spb > out_base + produced) ? spb - out_base - produced : 0u;
+        const uint32_t steps = min((uint32_t)(G::TB - pos) / G::STEP_BYTES, (left + G::SPS - 1u) / G::SPS);
         for (uint32_t s = 0; s < steps; s++) {
           if (BITS == 3) {
             uint32_t x[3];
@@ -532,7 +534,11 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
        * samples per turn so the shared output row takes whole 8-byte pieces */
       {
         const unsigned char *bp = irow + pos + GB * ch;
-        const uint32_t groups = (TB - pos) / gstride;          /* even for 4-bit in every window */
+        /* whole window, or what is left of the block's samples (the same in every lane); the 4-bit loop takes
+         * groups in pairs and may run one group past that, still inside the window */
+        constexpr uint32_t GS = (BITS == 4) ? 2 : (BITS == 3 ? 8 : 4);
+        const uint32_t left = (spb > out_base + produced) ? spb - out_base - produced : 0u;
+        const uint32_t groups = min((TB - pos) / gstride, (left + GS - 1u) / GS);
         if (BITS == 4) {
 #pragma unroll 2
           for (uint32_t g = 0; g < groups; g += 2) {
