@@ -230,7 +230,9 @@ static void wav_input_release(struct wav_input *w)
   memset(w, 0, sizeof(*w));
 }
 
-static int wav_input_open(const char *name, struct wav_input *w)
+/* need_pcm16: also provide the samples as interleaved int16 (host conversion for 8 / 24 / 32-bit files); paths that
+ * hand the data chunk to the device as it is (AADGpu_EncodeWav, AADGpu_AnalyzeWav) do not need it */
+static int wav_input_open(const char *name, struct wav_input *w, int need_pcm16)
 {
   memset(w, 0, sizeof(*w));
   w->image = read_file(name, &w->size);
@@ -244,7 +246,7 @@ static int wav_input_open(const char *name, struct wav_input *w)
   const uint8_t *data = w->image + w->info.data_offset;
   if (w->info.bits_per_sample == 16 && ((uintptr_t)data & 1u) == 0) {
     w->pcm16 = (int16_t *)(void *)data;            /* little-endian host: the data chunk IS the int16 array */
-  } else {
+  } else if (need_pcm16) {
     w->pcm16 = (int16_t *)io_alloc(count * sizeof(int16_t));
     if (w->pcm16 == NULL) { wav_input_release(w); return 1; }
     w->owns_pcm16 = 1;
@@ -305,7 +307,10 @@ static int execute_encode(struct AADGpu *gpu, const char *in_name, const char *o
 {
   struct wav_input w;
   struct AADEncodeParameter prm;
-  if (wav_input_open(in_name, &w) != 0) return 1;
+  /* several devices share ONE file's encode only in segment mode (--segment-blocks); otherwise one device does it */
+  const uint32_t seg = AADGpu_GetEncodeSegmentBlocks(gpu);
+  const int shared = (g_group != NULL && seg != 0);
+  if (wav_input_open(in_name, &w, shared) != 0) return 1;
   fill_parameter(&prm, cli, &w.info);
   const uint64_t bound = AADGpu_StreamBytesBound(&prm, w.info.num_samples);
   if (bound == 0 || bound > 0xFFFFFFFFull) {
@@ -317,11 +322,11 @@ static int execute_encode(struct AADGpu *gpu, const char *in_name, const char *o
   uint32_t out_size = 0;
   int rc = 1;
   if (data != NULL) {
-    /* several devices share ONE file's encode only in segment mode (--segment-blocks); otherwise device 0 does it */
-    const uint32_t seg = AADGpu_GetEncodeSegmentBlocks(gpu);
-    const AADApiResult r = (g_group != NULL && seg != 0)
+    /* one device: the data chunk goes up as it lies in the file, whatever its bit depth (src/main.c:175-179 on the device) */
+    const AADApiResult r = shared
         ? AADGpuGroup_EncodeInterleaved16(g_group, &prm, seg, w.pcm16, w.info.num_samples, data, (uint32_t)bound, &out_size)
-        : AADGpu_EncodeInterleaved16(gpu, &prm, w.pcm16, w.info.num_samples, data, (uint32_t)bound, &out_size);
+        : AADGpu_EncodeWav(gpu, &prm, w.image + w.info.data_offset, w.info.bits_per_sample, w.info.num_samples, data,
+                           (uint32_t)bound, &out_size);
     if (r != AAD_APIRESULT_OK) fprintf(stderr, "Failed to encode. API result:%d %s\n", r, AADGpu_LastError());
     else rc = write_file(out_name, data, out_size);
     io_free(data);
@@ -370,7 +375,7 @@ static int execute_analysis(struct AADGpu *gpu, int mode, const char *in_name, c
    * decode and the per-sample arithmetic of the mode run there (AADGpu_AnalyzeWav) */
   struct wav_input w;
   struct AADEncodeParameter prm;
-  if (wav_input_open(in_name, &w) != 0) return 1;
+  if (wav_input_open(in_name, &w, 0) != 0) return 1;
   fill_parameter(&prm, cli, &w.info);
   const uint32_t bits = w.info.bits_per_sample, C = w.info.num_channels, n = w.info.num_samples;
   const size_t count = (size_t)n * C;
@@ -449,7 +454,7 @@ static int execute_encode_batch(struct AADGpu *gpu, const char *manifest, const 
   int failures = 0;
   if (read_manifest(manifest, &items, &count) != 0) return 1;
   for (size_t i = 0; i < count; i++)
-    if (wav_input_open(items[i].in_name, &items[i].wav) != 0) { items[i].done = items[i].failed = 1; failures++; }
+    if (wav_input_open(items[i].in_name, &items[i].wav, 1) != 0) { items[i].done = items[i].failed = 1; failures++; }
   /* one AADGpu_EncodeBatch per (channels, sampling rate): lengths may be ragged inside a batch */
   for (size_t lead = 0; lead < count; lead++) {
     if (items[lead].done) continue;

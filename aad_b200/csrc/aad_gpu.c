@@ -839,9 +839,22 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
 
 /* src/main.c:175-179 + AADEncoder_EncodeWhole, with the de-interleave done on the device: the
  * samples of a 16-bit WAV data chunk go to HBM as they are.  Leaves the stream at gpu->aad + 1. */
+static AADApiResult encode_wav_device(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                      const struct aadf_geometry *geo, const void *interleaved, uint32_t wav_bits,
+                                      uint32_t num_samples, uint64_t *pitch_out, uint64_t *bytes_out);
+
 static AADApiResult encode_interleaved_device(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
                                               const struct aadf_geometry *geo, const int16_t *interleaved,
                                               uint32_t num_samples, uint64_t *pitch_out, uint64_t *bytes_out)
+{
+  return encode_wav_device(gpu, prm, geo, interleaved, 16, num_samples, pitch_out, bytes_out);
+}
+
+/* interleaved: the samples as they lie in a WAV data chunk of wav_bits bits per sample (16: plain int16), or NULL
+ * when the caller has put the planar int16 samples into gpu->pcm already (same pitch) */
+static AADApiResult encode_wav_device(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
+                                      const struct aadf_geometry *geo, const void *interleaved, uint32_t wav_bits,
+                                      uint32_t num_samples, uint64_t *pitch_out, uint64_t *bytes_out)
 {
   const uint32_t C = geo->channels;
   const uint64_t pitch = round_up64(num_samples, 64);
@@ -850,11 +863,17 @@ static AADApiResult encode_interleaved_device(struct AADGpu *gpu, const struct A
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
   cudaStream_t s = gpu->s_run;
-  if (interleaved != NULL) {   /* NULL: the caller has put the planar samples into gpu->pcm already (same pitch) */
+  if (interleaved != NULL && wav_bits == 16) {
     if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * num_samples * 2)) return AAD_APIRESULT_NG;
     CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved, (size_t)C * num_samples * 2, cudaMemcpyHostToDevice, s), "H2D wav");
     CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s),
        "deinterleave kernel launch");
+  } else if (interleaved != NULL) {   /* 8 / 24 / 32-bit chunk: narrowed to its top 16 bits while de-interleaving */
+    const size_t raw_bytes = (size_t)C * num_samples * (wav_bits / 8);
+    if (!aadgpu_reserve(gpu, &gpu->raw, raw_bytes)) return AAD_APIRESULT_NG;
+    CU(cudaMemcpyAsync(gpu->raw.ptr, interleaved, raw_bytes, cudaMemcpyHostToDevice, s), "H2D wav data");
+    CU((cudaError_t)aadk_launch_wav_to_planar16((const uint8_t *)gpu->raw.ptr, wav_bits, (int16_t *)gpu->pcm.ptr, pitch, C,
+                                                num_samples, s), "wav_to_planar16 kernel launch");
   }
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)bound + 128, s), "memset aad");
   struct aadk_encode_params p;
@@ -906,6 +925,40 @@ AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEnco
   if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
   pthread_mutex_lock(&gpu->lock);
   const AADApiResult r = AADGpu_EncodeInterleaved16_unlocked(gpu, prm, interleaved, num_samples, data, data_size, output_size);
+  pthread_mutex_unlock(&gpu->lock);
+  return r;
+}
+
+static AADApiResult AADGpu_EncodeWav_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
+                                              uint32_t wav_bits_per_sample, uint32_t num_samples, uint8_t *data,
+                                              uint32_t data_size, uint32_t *output_size)
+{
+  if (!gpu || !prm || !wav_data || !data || !output_size) return AAD_APIRESULT_INVALID_ARGUMENT;
+  const uint32_t wb = wav_bits_per_sample;
+  if (wb != 8 && wb != 16 && wb != 24 && wb != 32) return AAD_APIRESULT_INVALID_FORMAT;   /* src/wav.c:222-238 */
+  struct aadf_geometry geo;
+  const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
+  if (r != AAD_APIRESULT_OK) return r;
+  if (data_size < AADF_FILE_HEADER_BYTES) return AAD_APIRESULT_INSUFFICIENT_DATA;
+  if (aadf_stream_bytes(num_samples, geo.channels, geo.bits, geo.block_size, geo.samples_per_block) > data_size)
+    return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  uint64_t pitch = 0, bytes = 0;
+  const AADApiResult e = encode_wav_device(gpu, prm, &geo, wav_data, wb, num_samples, &pitch, &bytes);
+  if (e != AAD_APIRESULT_OK) return e;
+  CU(cudaMemcpyAsync(data, (uint8_t *)gpu->aad.ptr + 1, (size_t)bytes, cudaMemcpyDeviceToHost, gpu->s_run), "D2H aad");
+  CU(cudaStreamSynchronize(gpu->s_run), "sync");
+  *output_size = (uint32_t)bytes;
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_EncodeWav(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
+                              uint32_t wav_bits_per_sample, uint32_t num_samples, uint8_t *data, uint32_t data_size,
+                              uint32_t *output_size)
+{
+  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
+  pthread_mutex_lock(&gpu->lock);
+  const AADApiResult r = AADGpu_EncodeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, data, data_size, output_size);
   pthread_mutex_unlock(&gpu->lock);
   return r;
 }
@@ -1065,12 +1118,13 @@ static AADApiResult AADGpu_AnalyzeWav_unlocked(struct AADGpu *gpu, const struct 
   if (!aadgpu_reserve(gpu, &gpu->raw, raw_bytes)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * in_pitch * 2)) return AAD_APIRESULT_NG;
   cudaStream_t s = gpu->s_run;
-  /* the data chunk goes up as it lies in the file; narrowing to 16 bits and de-interleaving in one kernel */
+  /* the data chunk goes up as it lies in the file and stays in gpu->raw for the mode's arithmetic; narrowing to
+   * 16 bits and de-interleaving in one kernel */
   CU(cudaMemcpyAsync(gpu->raw.ptr, wav_data, raw_bytes, cudaMemcpyHostToDevice, s), "H2D wav data");
   CU((cudaError_t)aadk_launch_wav_to_planar16((const uint8_t *)gpu->raw.ptr, wb, (int16_t *)gpu->pcm.ptr, in_pitch, C, num_samples, s),
      "wav_to_planar16 kernel launch");
   uint64_t pitch = 0, bytes = 0;
-  AADApiResult e = encode_interleaved_device(gpu, prm, &geo, NULL, num_samples, &pitch, &bytes);
+  AADApiResult e = encode_wav_device(gpu, prm, &geo, NULL, 16, num_samples, &pitch, &bytes);
   if (e != AAD_APIRESULT_OK) return e;
   struct AADHeaderInfo h;
   header_of(prm, &geo, num_samples, &h);

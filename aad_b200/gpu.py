@@ -35,7 +35,7 @@ class GpuApi:
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_ReconstructBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
         "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath", "AADGpu_SetEncoderPairing",
         "AADGpu_SetEncodeSegmentBlocks", "AADGpu_GetEncodeSegmentBlocks",
-        "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16", "AADGpu_AnalyzeWav",
+        "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16", "AADGpu_AnalyzeWav", "AADGpu_EncodeWav",
         "AADGpuGroup_Create", "AADGpuGroup_Destroy", "AADGpuGroup_Size", "AADGpuGroup_Device",
         "AADGpuGroup_EncodeBatch", "AADGpuGroup_DecodeBatch", "AADGpuGroup_DecodeInterleaved16",
         "AADGpuGroup_EncodeInterleaved16",
@@ -74,6 +74,7 @@ class GpuApi:
             "AADGpu_EncodeInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, u32, C.POINTER(u32)]),
             "AADGpu_DecodeInterleaved16": (C.c_int, [vp, vp, u32, vp, u32]),
             "AADGpu_ReconstructInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, C.POINTER(u32)]),
+            "AADGpu_EncodeWav": (C.c_int, [vp, pp, vp, u32, u32, vp, u32, C.POINTER(u32)]),
             "AADGpu_AnalyzeWav": (C.c_int, [vp, pp, vp, u32, u32, C.c_int, vp, C.POINTER(C.c_double), C.POINTER(u32)]),
             "AADGpuGroup_Create": (vp, [C.POINTER(C.c_int), C.c_int]),
             "AADGpuGroup_Destroy": (None, [vp]),

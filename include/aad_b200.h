@@ -162,6 +162,13 @@ AADApiResult AADGpuGroup_EncodeInterleaved16(struct AADGpuGroup *group, const st
                                              uint32_t segment_blocks, const int16_t *interleaved, uint32_t num_samples,
                                              uint8_t *data, uint32_t data_size, uint32_t *output_size);
 
+/* AADGpu_EncodeInterleaved16 for a WAV data chunk of any supported depth (8 / 16 / 24 / 32 bits per sample, as it
+ * lies in the file): the codec sees the top 16 bits of every sample, (int16_t)(PCM >> 16) of src/main.c:175-179 with
+ * the widening of src/wav.c:391-415, computed on the device while de-interleaving. */
+AADApiResult AADGpu_EncodeWav(struct AADGpu *gpu, const struct AADEncodeParameter *param, const uint8_t *wav_data,
+                              uint32_t wav_bits_per_sample, uint32_t num_samples, uint8_t *data, uint32_t data_size,
+                              uint32_t *output_size);
+
 /* ---- the command line's analysis modes on the device, src/main.c:275-503 ------------------- */
 enum AADGpuAnalysis {
   AADGPU_ANALYSIS_RECONSTRUCT = 0,   /* -r: encode -> decode, written in the input's sample format (src/main.c:372-381) */

@@ -318,6 +318,10 @@ def test_analyze_wav_api_against_numpy_model(product, gpu_ctx, oracle, bits, cha
     size = C.c_uint32(0)
     assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 0, out.ctypes.data, None, C.byref(size)) == OK, gpu.last_error()
     assert size.value == len(data) and out.tobytes() == narrow(recon32)
+    enc = np.zeros(len(data) + 16, dtype=np.uint8)                               # AADGpu_EncodeWav: same chunk -> the oracle's stream
+    assert gpu.lib.AADGpu_EncodeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, enc.ctypes.data, len(enc), C.byref(size)) == OK
+    assert enc[:size.value].tobytes() == data
+    assert gpu.lib.AADGpu_EncodeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, enc.ctypes.data, 100, C.byref(size)) == 3   # INSUFFICIENT_BUFFER
     assert gpu.lib.AADGpu_AnalyzeWav(gpu_ctx, C.byref(prm), src.ctypes.data, bits, n, 1, out.ctypes.data, None, None) == OK
     assert out.tobytes() == narrow(pcm32 - recon32)
     stats = (C.c_double * 3)()
