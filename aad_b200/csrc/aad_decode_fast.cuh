@@ -577,15 +577,14 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
       /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
       if (all_full) {
         if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+          /* row = (block, channel): channels step by the plane pitch, blocks by spb samples */
           const unsigned char *srow = out_rows + 8u * lane;
           int16_t *dst_blk = grow0 + out_base + 4u * lane;
-          int16_t *dst = dst_blk;
-          uint32_t rch = 0;
+          for (uint32_t rb = 0; rb < rows; rb++, dst_blk += spb) {
+            int16_t *dst = dst_blk;
 #pragma unroll 4
-          for (uint32_t rr = 0; rr < active; rr++) {
-            *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
-            dst += p.pcm_ch_stride;
-            if (++rch == C) { rch = 0; dst_blk += spb; dst = dst_blk; }
+            for (uint32_t rc = 0; rc < C; rc++, dst += p.pcm_ch_stride, srow += kDecOutPitch)
+              *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow);
           }
         }
       } else {
