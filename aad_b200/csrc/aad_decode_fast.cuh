@@ -184,14 +184,17 @@ __device__ __forceinline__ uint4 dec_fetch16(const uint8_t *q, const uint8_t *en
  * short output buffers, missing data): row rr of the shared output rows holds `produced` samples of the chain
  * in lane rr, of which those below that chain's n_row go to its global row, as one coalesced run of 8-byte
  * pieces plus a scalar tail. */
-__device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, uint32_t rows, uint32_t n_row,
+__device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, uint32_t first, uint32_t rows, uint32_t n_row,
                                                  uint32_t produced, int16_t *grow, uint32_t out_base, uint32_t lane)
 {
-  for (uint32_t rr = 0; rr < rows; rr++) {
+  /* rows [first, rows) that still deliver samples in this window */
+  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & (rows < 32u ? (1u << rows) - 1u : 0xFFFFFFFFu) &
+                  ~(first < 32u ? (1u << first) - 1u : 0xFFFFFFFFu);
+  for (; live != 0u; live &= live - 1u) {
+    const uint32_t rr = (uint32_t)__ffs((int)live) - 1u;
     const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
     const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
     const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
-    if (n_rr <= out_base) continue;                       /* uniform */
     const uint32_t count = min(made, n_rr - out_base);
     int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
     const unsigned char *srow = out_rows + rr * kDecOutPitch;
@@ -241,7 +244,10 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;   /* samples this chain delivers */
     int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
     int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;   /* row 0 of the warp */
-    const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb);
+    /* rows [0, nfull) deliver whole blocks (all 32 but in a stream's last warp task); nfull is a multiple of C
+     * because the channels of a block share its sample count */
+    const uint32_t nfull = (uint32_t)__ffs((int)~__ballot_sync(0xFFFFFFFFu, n_row == spb)) - 1u;   /* __ffs(0) - 1 wraps to all ones */
+    const bool all_full = nfull >= 32u;
 
     /* loader role: IN_LOADS 16-byte chunks per lane per window */
     const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
@@ -396,7 +402,15 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
                 *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
         }
       } else {
-        dec_flush_ragged(out_rows, 32u, n_row, produced, grow, out_base, lane);
+        /* the leading whole-block rows with arithmetic addresses, the rest one by one */
+        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst = grow0 + out_base + 4u * lane;
+          for (uint32_t rr = 0; rr < nfull; rr++)
+            *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
+                *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+        }
+        dec_flush_ragged(out_rows, nfull, 32u, n_row, produced, grow, out_base, lane);
       }
       out_base += produced;       /* identical in every lane */
       __syncwarp();
@@ -462,7 +476,9 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;
     int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
     int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;
-    const bool all_full = __all_sync(0xFFFFFFFFu, n_row == spb || !lane_on);
+    /* rows [0, nfull) deliver whole blocks; a multiple of C (the channels of a block share its sample count) */
+    const uint32_t nfull = min(active, (uint32_t)__ffs((int)~__ballot_sync(0xFFFFFFFFu, n_row == spb)) - 1u);
+    const bool all_full = nfull >= active;
 
     /* loader role */
     const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
@@ -574,22 +590,22 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
       }
       __syncwarp();
 
-      /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
-      if (all_full) {
-        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
-          /* row = (block, channel): channels step by the plane pitch, blocks by spb samples */
-          const unsigned char *srow = out_rows + 8u * lane;
-          int16_t *dst_blk = grow0 + out_base + 4u * lane;
-          for (uint32_t rb = 0; rb < rows; rb++, dst_blk += spb) {
-            int16_t *dst = dst_blk;
+      /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces.  The leading whole-block rows
+       * (all of them but in a stream's last warp task) have arithmetic addresses and one common count --
+       * `produced` (identical in every lane), clipped where the last window runs past the block; both are
+       * multiples of 4 -- the rest go one by one */
+      if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+        /* row = (block, channel): channels step by the plane pitch, blocks by spb samples */
+        const unsigned char *srow = out_rows + 8u * lane;
+        int16_t *dst_blk = grow0 + out_base + 4u * lane;
+        for (uint32_t rb = 0; rb < nfull / C; rb++, dst_blk += spb) {
+          int16_t *dst = dst_blk;
 #pragma unroll 4
-            for (uint32_t rc = 0; rc < C; rc++, dst += p.pcm_ch_stride, srow += kDecOutPitch)
-              *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow);
-          }
+          for (uint32_t rc = 0; rc < C; rc++, dst += p.pcm_ch_stride, srow += kDecOutPitch)
+            *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow);
         }
-      } else {
-        dec_flush_ragged(out_rows, active, n_row, produced, grow, out_base, lane);
       }
+      if (!all_full) dec_flush_ragged(out_rows, nfull, active, n_row, produced, grow, out_base, lane);
       out_base += produced;       /* identical in every lane */
       __syncwarp();
     }
