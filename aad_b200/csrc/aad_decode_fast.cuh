@@ -344,6 +344,9 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         /* the block's last window stops where the block's samples end (the same in every lane) */
         const uint32_t left = (spb > out_base + produced) ? spb - out_base - produced : 0u;
         const uint32_t steps = min((uint32_t)(G::TB - pos) / G::STEP_BYTES, (left + G::SPS - 1u) / G::SPS);
+        /* two words per turn where a step is one word: halves the loop's bookkeeping (a 3-bit step is 3 words
+         * = 32 samples already) */
+#pragma unroll(BITS == 3 ? 1 : 2)
         for (uint32_t s = 0; s < steps; s++) {
           if (BITS == 3) {
             uint32_t x[3];
