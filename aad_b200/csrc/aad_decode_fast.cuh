@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     const uint32_t b = b0 + row;
     const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
     const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
-    const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;   /* samples this chain delivers */
+    /* samples this chain delivers: what the output buffer still holds at the block's first sample */
+    const uint32_t n_row = (have && (uint64_t)b * spb < buf) ? min(spb, buf - b * spb) : 0u;
     int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
     int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;   /* row 0 of the warp */
     /* rows [0, nfull) deliver whole blocks (all 32 but in a stream's last warp task); nfull is a multiple of C
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
     const bool have = lane_on && b < p.block_end && (uint64_t)b * spb < ns &&
                       blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
-    const uint32_t n_row = have ? min(spb, buf - b * spb) : 0u;
+    const uint32_t n_row = (have && (uint64_t)b * spb < buf) ? min(spb, buf - b * spb) : 0u;
     int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
     int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;
     /* rows [0, nfull) deliver whole blocks; a multiple of C (the channels of a block share its sample count) */

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
   if (blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C > size) return;
   const uint32_t avail = (uint32_t)min((uint64_t)bs, (uint64_t)size - blk_off);
   const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+  if ((uint64_t)b * spb >= buf) return;   /* nothing of this block fits the output buffer */
   const uint32_t want = min(spb, buf - b * spb);
 
   const uint8_t *blk = slot + blk_off;
