@@ -97,3 +97,69 @@ def test_block_shards_cover_the_file():
     assert shards[-1].sample_end == ns
     for a, b in zip(shards, shards[1:]):
         assert a.block_end == b.block_begin and a.byte_end == b.byte_begin and a.sample_end == b.sample_begin
+
+
+def _segment_worker(rank, world, port, out_dir):
+    """One stream ENCODED by two ranks in the segment-parallel extension: every rank encodes its own segment range
+    (the oracle on a fresh handle per segment = what the CUDA kernel's segment chains do), rank 0 reassembles."""
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import aadtest
+    from aad_b200.shard import encode_segment_shard
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    oracle = aadtest.Oracle(ROOT / "oracle" / "liboracle.so")
+    ch, n, bits, seg_blocks = 2, 61_003, 4, 3
+    pcm = aadtest.signal("music", ch, n, seed=5)
+    _, bs, spb = oracle.geometry(1024, ch, bits)
+    _, whole = oracle.encode(pcm, 48000, bits, 1024, False, 0)          # only for the file header and the size
+    sh = encode_segment_shard(n, spb, bs, len(whole), seg_blocks, world, rank)
+    mine = bytearray()
+    for g in range(sh.segment_begin, sh.segment_end):
+        s0 = g * seg_blocks * spb
+        rc, seg = oracle.encode(pcm[:, s0:s0 + seg_blocks * spb], 48000, bits, 1024, False, 2)
+        assert rc == 0
+        mine += seg[31:]
+    if sh.block_begin == 0:
+        mine = bytearray(whole[:31]) + mine
+    assert len(mine) == sh.byte_end - sh.byte_begin
+    parts = [None] * world
+    dist.all_gather_object(parts, (sh.byte_begin, bytes(mine)))
+    if rank == 0:
+        out = bytearray(len(whole))
+        for begin, blob in parts:
+            out[begin:begin + len(blob)] = blob
+        want = bytearray(whole[:31])
+        for s0 in range(0, n, seg_blocks * spb):
+            want += oracle.encode(pcm[:, s0:s0 + seg_blocks * spb], 48000, bits, 1024, False, 2)[1][31:]
+        rc, dec, _ = oracle.decode(bytes(out))                           # a valid stream for the stock decoder
+        ok = bytes(out) == bytes(want) and rc == 0 and dec.shape == pcm.shape
+        (Path(out_dir) / "segments.txt").write_text("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_two_rank_segment_encode_reassembles_exactly(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_segment_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "segments.txt").read_text() == "ok"
+
+
+def test_segment_shards_cover_the_stream():
+    from aad_b200.shard import encode_segment_shard
+    ns, spb, bs = 172_800_000, 992, 1024          # BASELINE config 3
+    size = 31 + (ns // spb) * bs + 36 + ((ns % spb - 4 + 1) // 2) * 2
+    for world in (1, 2, 4, 8):
+        shards = [encode_segment_shard(ns, spb, bs, size, 64, world, r) for r in range(world)]
+        assert shards[0].byte_begin == 0 and shards[-1].byte_end == size and shards[-1].sample_end == ns
+        assert shards[-1].block_end == 174_194 and shards[-1].segment_end == (174_194 + 63) // 64
+        for a, b in zip(shards, shards[1:]):
+            assert a.segment_end == b.segment_begin and a.block_end == b.block_begin and a.block_end % 64 == 0
+            assert a.sample_end == b.sample_begin and a.byte_end == b.byte_begin
+    # fewer segments than ranks: the extra ranks get empty shards
+    few = [encode_segment_shard(3000, 992, 1024, 31 + 4 * 1024, 64, 4, r) for r in range(4)]
+    assert few[0].block_end == 4 and all(s.block_begin == s.block_end for s in few[1:])
+    with pytest.raises(ValueError):
+        encode_segment_shard(ns, spb, bs, size, 0, 2, 0)
