@@ -49,6 +49,17 @@ void AADGpu_SetMaxChannels(uint32_t n)
     if (e__ != cudaSuccess) return aadgpu_fail(what, e__); \
   } while (0)
 
+/* Every entry point that uses a context's streams and scratch buffers runs under that context's lock
+ * (aad_gpu_internal.h): the body is the *_unlocked function of the same name. */
+#define WITH_CONTEXT_LOCK(gpu, call)                               \
+  do {                                                             \
+    if (!(gpu)) return AAD_APIRESULT_INVALID_ARGUMENT;             \
+    pthread_mutex_lock(&(gpu)->lock);                              \
+    const AADApiResult locked_result_ = (call);                    \
+    pthread_mutex_unlock(&(gpu)->lock);                            \
+    return locked_result_;                                         \
+  } while (0)
+
 int AADGpu_DeviceCount(void)
 {
   int n = 0;
@@ -358,11 +369,7 @@ static AADApiResult AADGpu_SynthBatchDevice_unlocked(struct AADGpu *gpu, const s
 AADApiResult AADGpu_SynthBatchDevice(struct AADGpu *gpu, const struct AADGpuBatch *batch, uint32_t first_stream,
                                      int16_t *pcm_dev, void *stream)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_SynthBatchDevice_unlocked(gpu, batch, first_stream, pcm_dev, stream);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_SynthBatchDevice_unlocked(gpu, batch, first_stream, pcm_dev, stream));
 }
 
 AADApiResult AADGpu_Deinterleave16Device(struct AADGpu *gpu, const int16_t *interleaved_dev, int16_t *planar_dev,
@@ -508,11 +515,7 @@ static AADApiResult AADGpu_EncodeBatch_unlocked(struct AADGpu *gpu, const struct
 AADApiResult AADGpu_EncodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
                                 const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_EncodeBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_EncodeBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes));
 }
 
 static AADApiResult AADGpu_DecodeBatch_unlocked(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad,
@@ -590,11 +593,7 @@ static AADApiResult AADGpu_DecodeBatch_unlocked(struct AADGpu *gpu, const struct
 AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const uint8_t *aad,
                                 const uint32_t *sizes, int16_t *pcm)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_DecodeBatch_unlocked(gpu, batch, aad, sizes, pcm);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_DecodeBatch_unlocked(gpu, batch, aad, sizes, pcm));
 }
 
 /* Encode a batch and decode it back in one pass over the data (what src/main.c:275-346 does for one
@@ -699,11 +698,7 @@ AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatc
                                      const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes,
                                      int16_t *reconstructed)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_ReconstructBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes, reconstructed);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_ReconstructBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes, reconstructed));
 }
 
 /* ---- single-stream paths behind the drop-in API ------------------------------------------- */
@@ -758,11 +753,7 @@ AADApiResult aadgpu_encode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
                                       uint32_t trials, const int32_t *const *input, uint32_t num_samples,
                                       int32_t *state, uint8_t *data, uint32_t *output_size)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = aadgpu_encode_stream_i32_unlocked(gpu, geo, sampling_rate, trials, input, num_samples, state, data, output_size);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, aadgpu_encode_stream_i32_unlocked(gpu, geo, sampling_rate, trials, input, num_samples, state, data, output_size));
 }
 
 static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *data,
@@ -828,11 +819,7 @@ AADApiResult aadgpu_decode_stream_i32(struct AADGpu *gpu, const struct aadf_geom
                                       uint32_t data_size, uint32_t num_blocks, uint32_t num_samples,
                                       uint32_t buf_samples, int32_t *const *buffer)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = aadgpu_decode_stream_i32_unlocked(gpu, geo, data, data_size, num_blocks, num_samples, buf_samples, buffer);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, aadgpu_decode_stream_i32_unlocked(gpu, geo, data, data_size, num_blocks, num_samples, buf_samples, buffer));
 }
 
 /* ---- WAV-order (interleaved int16) single-stream paths: what `aad -e / -d / -r` do ---------- */
@@ -922,11 +909,7 @@ AADApiResult AADGpu_EncodeInterleaved16(struct AADGpu *gpu, const struct AADEnco
                                         const int16_t *interleaved, uint32_t num_samples, uint8_t *data,
                                         uint32_t data_size, uint32_t *output_size)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_EncodeInterleaved16_unlocked(gpu, prm, interleaved, num_samples, data, data_size, output_size);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_EncodeInterleaved16_unlocked(gpu, prm, interleaved, num_samples, data, data_size, output_size));
 }
 
 static AADApiResult AADGpu_EncodeWav_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm, const uint8_t *wav_data,
@@ -956,11 +939,7 @@ AADApiResult AADGpu_EncodeWav(struct AADGpu *gpu, const struct AADEncodeParamete
                               uint32_t wav_bits_per_sample, uint32_t num_samples, uint8_t *data, uint32_t data_size,
                               uint32_t *output_size)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_EncodeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, data, data_size, output_size);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_EncodeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, data, data_size, output_size));
 }
 
 /* decode the stream at d_aad (device) into gpu->pcm (planar) and gpu->wav (interleaved) */
@@ -1032,11 +1011,7 @@ static AADApiResult AADGpu_DecodeInterleaved16_unlocked(struct AADGpu *gpu, cons
 AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
                                         int16_t *interleaved, uint32_t capacity_samples)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_DecodeInterleaved16_unlocked(gpu, data, data_size, interleaved, capacity_samples);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_DecodeInterleaved16_unlocked(gpu, data, data_size, interleaved, capacity_samples));
 }
 
 /* src/main.c:275-346 (execute_reconstruction_core): encode, then decode what was encoded; the
@@ -1075,11 +1050,7 @@ AADApiResult AADGpu_ReconstructInterleaved16(struct AADGpu *gpu, const struct AA
                                              const int16_t *interleaved, uint32_t num_samples,
                                              int16_t *reconstructed, uint32_t *encoded_size)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_ReconstructInterleaved16_unlocked(gpu, prm, interleaved, num_samples, reconstructed, encoded_size);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_ReconstructInterleaved16_unlocked(gpu, prm, interleaved, num_samples, reconstructed, encoded_size));
 }
 
 /* ---- the analysis modes of the command line, src/main.c:275-503, with the samples staying on the device -------- */
@@ -1160,11 +1131,7 @@ AADApiResult AADGpu_AnalyzeWav(struct AADGpu *gpu, const struct AADEncodeParamet
                                uint32_t wav_bits_per_sample, uint32_t num_samples, enum AADGpuAnalysis what,
                                uint8_t *out_data, double stats[3], uint32_t *encoded_size)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = AADGpu_AnalyzeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, what, out_data, stats, encoded_size);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, AADGpu_AnalyzeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, what, out_data, stats, encoded_size));
 }
 
 /* ---- several devices of one box: shard, run one host thread per device, done ---------------- */
@@ -1398,11 +1365,7 @@ static AADApiResult decode_stream_range_unlocked(struct AADGpu *gpu, const struc
 static AADApiResult decode_stream_range(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
                                         uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = decode_stream_range_unlocked(gpu, h, data, data_size, b0, b1, interleaved);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, decode_stream_range_unlocked(gpu, h, data, data_size, b0, b1, interleaved));
 }
 
 AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_t *data, uint32_t data_size,
@@ -1505,11 +1468,7 @@ static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEnco
                                         const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
                                         uint8_t *data)
 {
-  if (!gpu) return AAD_APIRESULT_INVALID_ARGUMENT;
-  pthread_mutex_lock(&gpu->lock);
-  const AADApiResult r = encode_stream_range_unlocked(gpu, prm, segment_blocks, interleaved, num_samples, b0, b1, data);
-  pthread_mutex_unlock(&gpu->lock);
-  return r;
+  WITH_CONTEXT_LOCK(gpu, encode_stream_range_unlocked(gpu, prm, segment_blocks, interleaved, num_samples, b0, b1, data));
 }
 
 AADApiResult AADGpuGroup_EncodeInterleaved16(struct AADGpuGroup *g, const struct AADEncodeParameter *prm,
