@@ -23,11 +23,31 @@ def test_library_exports_every_declared_symbol(product):
     declared = set()
     for header in (ROOT / "include").glob("*.h"):
         text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
-        declared |= set(re.findall(r"\b(AAD(?:Encoder|Decoder|Gpu)_\w+)\s*\(", text))
+        declared |= set(re.findall(r"\b(AAD(?:Encoder|Decoder|Gpu|GpuGroup)_\w+)\s*\(", text))
     assert len(declared) >= 14 + 15
     for name in sorted(declared):
         assert hasattr(api.lib, name), f"{name} declared in include/ but not exported"
     assert set(api.SYMBOLS) <= declared
+    assert set(gpu.SYMBOLS) <= declared
+
+
+def test_ctypes_bindings_match_the_header_prototypes(product):
+    """Every prototype of include/aad_b200.h that aad_b200/gpu.py binds takes as many arguments as the binding
+    passes (a drifted binding would corrupt the call instead of failing)."""
+    _, gpu = product
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "aad_b200.h").read_text(), flags=re.S)
+    arity = {}
+    for name, params in re.findall(r"\b(AADGpu(?:Group)?_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        arity[name] = 0 if params in ("", "void") else params.count(",") + 1
+    checked = 0
+    for name in gpu.SYMBOLS:
+        fn = getattr(gpu.lib, name)
+        if fn.argtypes is None or name not in arity:
+            continue
+        assert len(fn.argtypes) == arity[name], (name, len(fn.argtypes), arity[name])
+        checked += 1
+    assert checked >= 25
 
 
 @pytest.mark.parametrize("max_block,ch,bits,bs,spb", BLOCK_SIZE_KAT)
