@@ -1,7 +1,9 @@
 /*
  * aad_encode_fast.cuh -- the production encoder kernel (included by aad_kernels.cu).
  *
- * A chain = one (stream, channel).  The reference carries the predictor weights and the step
+ * A chain = one (stream, channel) -- or, in the segment-parallel extension (aad_kernels.h:
+ * segment_blocks), one (stream, segment, channel), a segment being a run of blocks that is encoded
+ * like a stream of its own.  The reference carries the predictor weights and the step
  * index from block to block (processor[], src/aad_encoder.c:21,853-886), so a chain is serial over
  * its blocks; per block it runs the start-state search (src/aad_encoder.c:470-562: 1 + 2*trials
  * dry-run passes) and then the emitting pass (src/aad_encoder.c:565-727).  One thread per chain;
