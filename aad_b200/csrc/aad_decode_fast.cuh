@@ -184,8 +184,13 @@ __device__ __forceinline__ uint4 dec_fetch16(const uint8_t *q, const uint8_t *en
  * short output buffers, missing data): row rr of the shared output rows holds `produced` samples of the chain
  * in lane rr, of which those below that chain's n_row go to its global row, as one coalesced run of 8-byte
  * pieces plus a scalar tail. */
+/* mid / side -> left (M + S) or right (M - S), clipped to 16 bits (src/aad_decoder.c:458-470), on two packed samples */
+__device__ __forceinline__ uint32_t dec_ms2(uint32_t m, uint32_t s, bool right) { return right ? __vsubss2(m, s) : __vaddss2(m, s); }
+
+/* ms_pairs: rows 2k / 2k+1 hold the mid / side chains of one block and go out as its left / right channel */
 __device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, uint32_t first, uint32_t rows, uint32_t n_row,
-                                                 uint32_t produced, int16_t *grow, uint32_t out_base, uint32_t lane)
+                                                 uint32_t produced, int16_t *grow, uint32_t out_base, uint32_t lane,
+                                                 bool ms_pairs = false)
 {
   /* rows [first, rows) that still deliver samples in this window */
   uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & (rows < 32u ? (1u << rows) - 1u : 0xFFFFFFFFu) &
@@ -199,11 +204,35 @@ __device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, 
     int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
     const unsigned char *srow = out_rows + rr * kDecOutPitch;
     const uint32_t s0 = lane * 4u;
-    if (s0 + 4u <= count) {
+    if (ms_pairs) {
+      const unsigned char *mrow = out_rows + (rr & ~1u) * kDecOutPitch, *trow = out_rows + (rr | 1u) * kDecOutPitch;
+      const bool right = (rr & 1u) != 0u;
+      if (s0 + 4u <= count) {
+        const uint2 m = *reinterpret_cast<const uint2 *>(mrow + 2u * s0), t = *reinterpret_cast<const uint2 *>(trow + 2u * s0);
+        *reinterpret_cast<uint2 *>(dst + s0) = make_uint2(dec_ms2(m.x, t.x, right), dec_ms2(m.y, t.y, right));
+      } else {
+        for (uint32_t k = s0; k < count; k++) {
+          const int32_t m = *reinterpret_cast<const int16_t *>(mrow + 2u * k), t = *reinterpret_cast<const int16_t *>(trow + 2u * k);
+          dst[k] = (int16_t)max(-32768, min(32767, right ? m - t : m + t));
+        }
+      }
+    } else if (s0 + 4u <= count) {
       *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
     } else {
       for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
     }
+  }
+}
+
+/* the whole-block rows [0, nrows) of a stereo mid/side warp task: rows 2k / 2k+1 -> left / right plane of block k */
+__device__ __forceinline__ void dec_flush_ms_rows(const unsigned char *srow, int16_t *dst, uint32_t nrows, uint64_t ch_stride,
+                                                  uint32_t spb)
+{
+  for (uint32_t rr = 0; rr < nrows; rr += 2, dst += spb) {
+    const uint2 m = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+    const uint2 t = *reinterpret_cast<const uint2 *>(srow + (rr + 1u) * kDecOutPitch);
+    *reinterpret_cast<uint2 *>(dst) = make_uint2(dec_ms2(m.x, t.x, false), dec_ms2(m.y, t.y, false));
+    *reinterpret_cast<uint2 *>(dst + ch_stride) = make_uint2(dec_ms2(m.x, t.x, true), dec_ms2(m.y, t.y, true));
   }
 }
 
@@ -225,6 +254,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint32_t warps_per_stream = (nblocks + G::IN_ROWS - 1) / G::IN_ROWS;
   const uint64_t total_warps = (uint64_t)p.num_streams * warps_per_stream;
+  const bool ms2 = (C == 2) && p.geo.ms != 0u;   /* mid/side stereo: left / right formed in the flush */
   /* persistent: the warps of the grid share out the warp tasks round robin (the tables are built once per CTA) */
   for (uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp; gw < total_warps; gw += (uint64_t)gridDim.x * kDecWarps) {
     const uint64_t stream = gw / warps_per_stream;
@@ -393,7 +423,12 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       __syncwarp();
 
       /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
-      if (all_full) {
+      if (ms2) {
+        /* stereo mid/side: the left / right planes are formed here, from the two rows of a block (src/aad_decoder.c:458-470) */
+        if (lane * 4u + 4u <= min(produced, spb - out_base))
+          dec_flush_ms_rows(out_rows + 8u * lane, grow0 + out_base + 4u * lane, min(nfull, 32u), p.pcm_ch_stride, spb);
+        if (!all_full) dec_flush_ragged(out_rows, nfull, 32u, n_row, produced, grow, out_base, lane, true);
+      } else if (all_full) {
         /* every chain of the warp delivers a whole block: row addresses are plain arithmetic and the
          * count is the same for every row -- `produced` (identical in every lane), clipped where the
          * last window runs past the block; both are multiples of 4 */

@@ -575,7 +575,9 @@ int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
     }
   }
   g_launches++;
-  if (p->geo.ms && p->geo.channels >= 2) {
+  /* mid/side -> left/right: inside aad_decode_fast's flush for stereo, a pass of its own after the other kernels */
+  const bool fused_ms = dec_fast_eligible(*p) && !g_force_generic && p->geo.channels == 2 && !g_dec_wide_all;
+  if (p->geo.ms && p->geo.channels >= 2 && !fused_ms) {
     const uint64_t n = (uint64_t)p->num_streams * (p->block_end - p->block_begin) * p->geo.samples_per_block;
     aad_ms_to_lr<<<grid_for(n, 256), 256, 0, s>>>(*p);
     g_launches++;
