@@ -350,6 +350,18 @@ static int execute_decode(struct AADGpu *gpu, const char *in_name, const char *o
     io_free(data);
     return 1;
   }
+  /* validate the header before it sizes an allocation: AADDecoder_SetHeader applies the format checks of
+   * src/aad_decoder.c:173-225 (what the reference's DecodeWhole does first, src/aad_decoder.c:499) */
+  {
+    struct AADDecoder *probe = AADDecoder_Create(NULL, 0);
+    r = (probe != NULL) ? AADDecoder_SetHeader(probe, &h) : AAD_APIRESULT_NG;
+    AADDecoder_Destroy(probe);
+    if (r != AAD_APIRESULT_OK) {
+      fprintf(stderr, "Failed to decode. API result: %d \n", r);
+      io_free(data);
+      return 1;
+    }
+  }
   /* the output file image: 44-byte header, then the decoder's interleaved int16 land in place */
   const size_t count = (size_t)h.num_channels * h.num_samples;
   uint8_t *image = (uint8_t *)io_alloc(AADWAV_HEADER_BYTES + count * 2 + 2);

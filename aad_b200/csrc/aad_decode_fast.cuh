@@ -236,7 +236,81 @@ __device__ __forceinline__ void dec_flush_ms_rows(const unsigned char *srow, int
   }
 }
 
-template <int BITS, int C>
+/* ---- WAV-order output (aadk_decode_params::interleaved): the flush forms whole frames ---------------------- */
+
+/* Four consecutive frames of one block: rows srow, srow + pitch, ... hold the CH channels of the block (8 bytes =
+ * this lane's 4 samples of each), dst = the first of the lane's 4 frames (4 * CH * 2 bytes, 16-byte aligned for
+ * CH >= 2).  ms: rows 0 / 1 are mid / side (src/aad_decoder.c:458-470). */
+template <int CH>
+__device__ __forceinline__ void dec_flush_frames4(const unsigned char *srow, int16_t *dst, bool ms)
+{
+  uint2 m[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) m[c] = *reinterpret_cast<const uint2 *>(srow + c * kDecOutPitch);
+  if (ms) {
+    const uint2 mid = m[0], side = m[1];
+    m[0] = make_uint2(dec_ms2(mid.x, side.x, false), dec_ms2(mid.y, side.y, false));
+    m[1] = make_uint2(dec_ms2(mid.x, side.x, true), dec_ms2(mid.y, side.y, true));
+  }
+  /* 16 bytes at a time: 8 / CH frames of CH / 2 channel pairs each (few live registers: 8 channels would otherwise
+   * hold 32) */
+  constexpr int FPG = 8 / CH;
+#pragma unroll
+  for (int g = 0; g < 4 / FPG; g++) {
+    uint32_t w[4];
+#pragma unroll
+    for (int ff = 0; ff < FPG; ff++) {
+      const int f = g * FPG + ff;
+#pragma unroll
+      for (int j = 0; j < CH / 2; j++) {
+        const uint32_t a = (f < 2) ? m[2 * j].x : m[2 * j].y, b = (f < 2) ? m[2 * j + 1].x : m[2 * j + 1].y;
+        w[ff * (CH / 2) + j] = __byte_perm(a, b, (f & 1) ? 0x7632 : 0x5410);
+      }
+    }
+    *reinterpret_cast<uint4 *>(dst + 8 * g) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+/* the same for blocks whose chains do not all deliver a whole block (see dec_flush_ragged): rows [first, rows),
+ * CH rows per block, every row of a block with the same count */
+template <int CH>
+__device__ __noinline__ void dec_flush_ragged_frames(const unsigned char *out_rows, uint32_t first, uint32_t rows,
+                                                        uint32_t n_row, uint32_t produced, int16_t *gframe,
+                                                        uint32_t out_base, uint32_t lane, bool ms)
+{
+  uint32_t heads = 0u;   /* lanes that hold channel 0 of a block */
+#pragma unroll
+  for (int k = 0; k < 32; k += CH) heads |= 1u << k;
+  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & heads & (rows < 32u ? (1u << rows) - 1u : 0xFFFFFFFFu) &
+                  ~(first < 32u ? (1u << first) - 1u : 0xFFFFFFFFu);
+  for (; live != 0u; live &= live - 1u) {
+    const uint32_t rr = (uint32_t)__ffs((int)live) - 1u;
+    const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+    const uint32_t made = __shfl_sync(0xFFFFFFFFu, produced, rr);
+    const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)gframe, rr);
+    const uint32_t count = min(made, n_rr - out_base);
+    int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + (uint64_t)out_base * CH;
+    const unsigned char *srow = out_rows + rr * kDecOutPitch;
+    const uint32_t s0 = lane * 4u;
+    if (s0 + 4u <= count) {
+      dec_flush_frames4<CH>(srow + 2u * s0, dst + (uint64_t)s0 * CH, ms);
+    } else {
+      for (uint32_t k = s0; k < count; k++) {
+        if (ms) {
+          const int32_t m = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+          const int32_t t = *reinterpret_cast<const int16_t *>(srow + kDecOutPitch + 2u * k);
+          dst[(uint64_t)k * CH] = (int16_t)max(-32768, min(32767, m + t));
+          dst[(uint64_t)k * CH + 1] = (int16_t)max(-32768, min(32767, m - t));
+        } else {
+#pragma unroll
+          for (int c = 0; c < CH; c++) dst[(uint64_t)k * CH + c] = *reinterpret_cast<const int16_t *>(srow + c * kDecOutPitch + 2u * k);
+        }
+      }
+    }
+  }
+}
+
+template <int BITS, int C, int IL>   /* IL = 1: stereo output in WAV order (frames), formed in the flush */
 __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_decode_params p)
 {
   using G = DecGeom<BITS, C>;
@@ -263,7 +337,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     const uint8_t *slot = p.aad + stream * p.aad_stride;
     const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
     uint32_t ns = p.uniform_samples;
-    if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+    if (p.read_headers) ns = dec_header_samples(slot, size, p.uniform_samples);
     const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
 
     /* this lane's chain */
@@ -273,15 +347,23 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
     /* samples this chain delivers: what the output buffer still holds at the block's first sample */
     const uint32_t n_row = (have && (uint64_t)b * spb < buf) ? min(spb, buf - b * spb) : 0u;
-    int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
-    int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;   /* row 0 of the warp */
+    /* rows of p.pcm start at sample p.sample_base, p.aad at byte p.byte_base of the stream (shards of one stream) */
+    const uint64_t srel = (uint64_t)b * spb - p.sample_base, srel0 = (uint64_t)b0 * spb - p.sample_base;
+    int16_t *grow, *grow0;   /* this chain's row / row 0 of the warp (IL: first frame of the block) */
+    if (IL) {
+      grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel * C;
+      grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel0 * C;
+    } else {
+      grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + srel;
+      grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel0;
+    }
     /* rows [0, nfull) deliver whole blocks (all 32 but in a stream's last warp task); nfull is a multiple of C
      * because the channels of a block share its sample count */
     const uint32_t nfull = (uint32_t)__ffs((int)~__ballot_sync(0xFFFFFFFFu, n_row == spb)) - 1u;   /* __ffs(0) - 1 wraps to all ones */
     const bool all_full = nfull >= 32u;
 
     /* loader role: IN_LOADS 16-byte chunks per lane per window */
-    const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;       /* first block of the warp */
+    const uint8_t *g0 = slot + (AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs - p.byte_base);       /* first block of the warp */
     const uint8_t *ld_ptr[G::IN_LOADS];
     uint32_t ld_smem[G::IN_LOADS];
 #pragma unroll
@@ -292,7 +374,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       ld_ptr[m] = (f < (uint32_t)(G::IN_ROWS * G::IN_CHUNKS)) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
       ld_smem[m] = rr * G::IN_PITCH + 16u * cc;
     }
-    const uint8_t *slot_end = slot + size;
+    const uint8_t *slot_end = slot + ((uint64_t)size > p.byte_base ? (uint64_t)size - p.byte_base : 0u);
     auto fetch = [&](int m) -> uint4 { return dec_fetch16(ld_ptr[m], slot_end); };
 
     /* reader role: this lane's block row in shared memory */
@@ -332,7 +414,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         const uint32_t hp = AADF_CHANNEL_HEADER_BYTES * ch;
         const uint32_t head = (in_u8(hp) << 8) | in_u8(hp + 1);
         c.idx = (int32_t)(int16_t)(head >> 4);
-        c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */    /* a corrupt header must not index outside the table */
+        c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
         const uint32_t shift = head & 0xFu;
         int32_t wv[4], hv[4];
 #pragma unroll
@@ -423,7 +505,17 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       __syncwarp();
 
       /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
-      if (ms2) {
+      if (IL) {
+        /* WAV order: the two rows of a block leave as frames, 16 bytes (4 frames) per lane and block */
+        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst = grow0 + (uint64_t)(out_base + 4u * lane) * C;
+          const uint32_t nrows = min(nfull, 32u);
+          for (uint32_t rr = 0; rr < nrows; rr += C, dst += (uint64_t)spb * C, srow += C * kDecOutPitch)
+            dec_flush_frames4<2>(srow, dst, ms2);
+        }
+        if (!all_full) dec_flush_ragged_frames<2>(out_rows, nfull, 32u, n_row, produced, grow, out_base, lane, ms2);
+      } else if (ms2) {
         /* stereo mid/side: the left / right planes are formed here, from the two rows of a block (src/aad_decoder.c:458-470) */
         if (lane * 4u + 4u <= min(produced, spb - out_base))
           dec_flush_ms_rows(out_rows + 8u * lane, grow0 + out_base + 4u * lane, min(nfull, 32u), p.pcm_ch_stride, spb);
@@ -468,7 +560,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
  * of the mono / stereo kernel's sliding words, everything else as there: 16-byte coalesced global
  * loads one window ahead, 8-byte shared output stores, coalesced 8-byte row stores to the PCM planes.
  */
-template <int BITS>
+template <int BITS, int IL>   /* IL = 1: output in WAV order (4 or 8 channels), frames formed in the flush */
 __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_decode_params p)
 {
   constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
@@ -502,7 +594,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     const uint8_t *slot = p.aad + stream * p.aad_stride;
     const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
     uint32_t ns = p.uniform_samples;
-    if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+    if (p.read_headers) ns = dec_header_samples(slot, size, p.uniform_samples);
     const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
 
     /* this lane's chain (idle lanes shadow row 0 and deliver nothing) */
@@ -513,14 +605,16 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
     const bool have = lane_on && b < p.block_end && (uint64_t)b * spb < ns &&
                       blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
     const uint32_t n_row = (have && (uint64_t)b * spb < buf) ? min(spb, buf - b * spb) : 0u;
-    int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
-    int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)b0 * spb;
+    constexpr bool il = IL != 0;   /* WAV order (C = 4 or 8 here: aadk_decode_interleaved_ok) */
+    const uint64_t srel = (uint64_t)b * spb - p.sample_base, srel0 = (uint64_t)b0 * spb - p.sample_base;
+    int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (il ? srel * C : (uint64_t)ch * p.pcm_ch_stride + srel);
+    int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (il ? srel0 * C : srel0);
     /* rows [0, nfull) deliver whole blocks; a multiple of C (the channels of a block share its sample count) */
     const uint32_t nfull = min(active, (uint32_t)__ffs((int)~__ballot_sync(0xFFFFFFFFu, n_row == spb)) - 1u);
     const bool all_full = nfull >= active;
 
     /* loader role */
-    const uint8_t *g0 = slot + AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
+    const uint8_t *g0 = slot + (AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs - p.byte_base);
     const uint8_t *ld_ptr[kLoads];
     uint32_t ld_smem[kLoads];
 #pragma unroll
@@ -531,7 +625,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
       ld_ptr[m] = (f < rows * chunks) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
       ld_smem[m] = rr * pitch + 16u * cc;
     }
-    const uint8_t *slot_end = slot + size;
+    const uint8_t *slot_end = slot + ((uint64_t)size > p.byte_base ? (uint64_t)size - p.byte_base : 0u);
     auto fetch = [&](int m) -> uint4 { return dec_fetch16(ld_ptr[m], slot_end); };
 
     /* reader role */
@@ -633,6 +727,21 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
        * (all of them but in a stream's last warp task) have arithmetic addresses and one common count --
        * `produced` (identical in every lane), clipped where the last window runs past the block; both are
        * multiples of 4 -- the rest go one by one */
+      if (il) {
+        /* WAV order: the C rows of a block leave as frames, 4 frames (8 C bytes) per lane and block */
+        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst = grow0 + (uint64_t)(out_base + 4u * lane) * C;
+          for (uint32_t rb = 0; rb < nfull / C; rb++, dst += (uint64_t)spb * C, srow += C * kDecOutPitch) {
+            if (C == 8) dec_flush_frames4<8>(srow, dst, false);
+            else dec_flush_frames4<4>(srow, dst, false);
+          }
+        }
+        if (!all_full) {
+          if (C == 8) dec_flush_ragged_frames<8>(out_rows, nfull, active, n_row, produced, grow, out_base, lane, false);
+          else dec_flush_ragged_frames<4>(out_rows, nfull, active, n_row, produced, grow, out_base, lane, false);
+        }
+      } else {
       if (lane * 4u + 4u <= min(produced, spb - out_base)) {
         /* row = (block, channel): channels step by the plane pitch, blocks by spb samples */
         const unsigned char *srow = out_rows + 8u * lane;
@@ -645,6 +754,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
         }
       }
       if (!all_full) dec_flush_ragged(out_rows, nfull, active, n_row, produced, grow, out_base, lane);
+      }
       out_base += produced;       /* identical in every lane */
       __syncwarp();
     }
@@ -655,7 +765,9 @@ inline bool dec_fast_eligible(const aadk_decode_params &p)
 {
   if (p.geo.channels < 1 || p.geo.channels > 32) return false;
   if (p.geo.samples_per_block % 4u) return false;
-  if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u)) return false;
+  if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (!p.interleaved && (p.pcm_ch_stride % 4u))) return false;
+  if (p.sample_base % 4u) return false;
+  if (p.interleaved && p.geo.channels > 1 && (((uintptr_t)p.pcm & 15u) || (p.pcm_clip_stride % 8u))) return false;
   /* the window arithmetic assumes the canonical block layout: header, then whole groups */
   const uint32_t gs = aadf_group_samples(p.geo.bits), gb = aadf_group_bytes(p.geo.bits);
   if (p.geo.samples_per_block < AADF_TAPS || (p.geo.samples_per_block - AADF_TAPS) % gs) return false;
@@ -683,19 +795,19 @@ int dec_persistent_grid(K kernel, size_t smem, uint64_t warps, unsigned *grid)
   return 0;
 }
 
-template <int BITS, int C>
+template <int BITS, int C, int IL>
 int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
 {
   using G = DecGeom<BITS, C>;
   const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * G::WARP_BYTES;
   /* per device, so not cached in a static: a process may drive several GPUs */
-  cudaError_t e = cudaFuncSetAttribute(aad_decode_fast<BITS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(aad_decode_fast<BITS, C, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
   unsigned grid = 0;
-  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C>, smem, warps, &grid)) return rc;
-  aad_decode_fast<BITS, C><<<grid, kDecWarps * 32, smem, s>>>(p);
+  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C, IL>, smem, warps, &grid)) return rc;
+  aad_decode_fast<BITS, C, IL><<<grid, kDecWarps * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -705,13 +817,14 @@ int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
   const uint32_t C = p.geo.channels, rows = 32u / C;
   const size_t in_bytes = ((size_t)rows * 16u * ((BITS * C + 1u) | 1u) + 16u + 15u) & ~(size_t)15;
   const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (in_bytes + 32u * kDecOutPitch);
-  cudaError_t e = cudaFuncSetAttribute(aad_decode_wide<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kernel = p.interleaved ? aad_decode_wide<BITS, 1> : aad_decode_wide<BITS, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + rows - 1) / rows);
   unsigned grid = 0;
-  if (int rc = dec_persistent_grid(aad_decode_wide<BITS>, smem, warps, &grid)) return rc;
-  aad_decode_wide<BITS><<<grid, kDecWarps * 32, smem, s>>>(p);
+  if (int rc = dec_persistent_grid(kernel, smem, warps, &grid)) return rc;
+  kernel<<<grid, kDecWarps * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -719,8 +832,9 @@ int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
 template <int BITS>
 int dec_fast_launch(const aadk_decode_params &p, cudaStream_t s)
 {
-  if (p.geo.channels > 2 || g_dec_wide_all) return dec_wide_launch<BITS>(p, s);
-  return p.geo.channels == 1 ? dec_fast_launch_bc<BITS, 1>(p, s) : dec_fast_launch_bc<BITS, 2>(p, s);
+  if (p.geo.channels > 2 || (g_dec_wide_all && !p.interleaved)) return dec_wide_launch<BITS>(p, s);
+  if (p.geo.channels == 1) return dec_fast_launch_bc<BITS, 1, 0>(p, s);   /* mono: WAV order is the plane itself */
+  return p.interleaved ? dec_fast_launch_bc<BITS, 2, 1>(p, s) : dec_fast_launch_bc<BITS, 2, 0>(p, s);
 }
 
 }  // namespace

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   const uint32_t ns = p.num_samples ? p.num_samples[stream] : p.uniform_samples;
 
   uint8_t *out = p.aad + stream * p.aad_stride;
-  if (ch == 0 && seg == 0 && p.block_begin == 0) {
+  if (ch == 0 && seg == 0 && p.block_begin == 0 && p.byte_base == 0) {
     if (ns > 0) aadf_write_file_header(out, C, ns, p.sampling_rate, BITS, bs, spb, p.geo.ms);
     if (p.out_sizes) p.out_sizes[stream] = ns ? (uint32_t)aadf_stream_bytes(ns, C, BITS, bs, spb) : 0u;
   }
@@ -572,8 +572,10 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   /* this chain's blocks: [seg_first, seg_end) cut to the launch's block range */
   const uint32_t seg_first = p.segment_blocks ? seg * p.segment_blocks : 0u;
   const uint32_t seg_end = p.segment_blocks ? seg_first + p.segment_blocks : 0xFFFFFFFFu;
-  const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), p.block_end), seg_end);
-  const uint32_t b_begin = max(p.block_begin, seg_first);
+  /* the launch's block range counts from the stream's first block, or (segment_relative) from every segment's */
+  const uint32_t rel = (p.segment_blocks && p.segment_relative) ? seg_first : 0u;
+  const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), (uint32_t)min((uint64_t)rel + p.block_end, (uint64_t)0xFFFFFFFFu)), seg_end);
+  const uint32_t b_begin = max(rel + p.block_begin, seg_first);
   if (p.segment_blocks && b_begin == seg_first) S.w0 = S.w1 = S.w2 = S.w3 = S.idx8 = 0;   /* a segment starts like a new stream */
 
   EncJob<MS> job, job2;
@@ -582,8 +584,8 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   job2.ring.base = job.ring.base + EncRing<MS>::kWarpBytes;
 
   for (uint32_t b = b_begin; b < nblk; b++) {
-    const uint32_t first = b * spb;
-    const uint32_t n = min(spb, ns - first);
+    const uint32_t n = min(spb, ns - b * spb);
+    const uint32_t first = b * spb - (uint32_t)p.sample_base;   /* the rows of p.pcm start at sample sample_base */
     /* src/aad_encoder.c:470-562 then :565-727, as one loop over passes (a single copy of the
      * sample loop in the instruction stream):
      *   pass 0        baseline: current block from the carried state
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
       job.n = on_prev ? spb : n;
       job.run = true;
       job.emit = emit;
-      job.blk = out + AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+      job.blk = out + (AADF_FILE_HEADER_BYTES + (uint64_t)b * bs - p.byte_base);   /* p.aad points at byte byte_base */
       enc_run_job<BITS, MS>(job, src, ch, C, sh);
       if (emit) {
         S = job.c.state();
@@ -644,7 +646,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
 inline bool enc_fast_eligible(const aadk_encode_params &p)
 {
   if (p.geo.samples_per_block % 4u) return false;
-  if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u)) return false;
+  if (((uintptr_t)p.pcm & 7u) || (p.pcm_clip_stride % 4u) || (p.pcm_ch_stride % 4u) || (p.sample_base % 4u)) return false;
   return true;
 }
 

@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 static __thread char tl_error[320] = "";
 static uint32_t g_max_channels = AADF_MAX_CHANNELS;
@@ -43,10 +44,24 @@ void AADGpu_SetMaxChannels(uint32_t n)
   if (n >= 1 && n <= AADF_MAX_CHANNELS) g_max_channels = n;
 }
 
+/* A failed CUDA call ends the entry point -- but never with copies or kernels still in flight on the caller's
+ * host buffers or on the context's scratch memory: the three pipeline streams are drained first, and the
+ * (possibly sticky) error state is read so the next call starts clean.  Every use has `gpu` in scope. */
+static AADApiResult aadgpu_fail_drained(struct AADGpu *g, const char *what, cudaError_t err)
+{
+  if (g) {
+    if (g->s_in) (void)cudaStreamSynchronize(g->s_in);
+    if (g->s_run) (void)cudaStreamSynchronize(g->s_run);
+    if (g->s_out) (void)cudaStreamSynchronize(g->s_out);
+  }
+  (void)cudaGetLastError();
+  return aadgpu_fail(what, err);
+}
+
 #define CU(call, what)                                  \
   do {                                                  \
     cudaError_t e__ = (call);                           \
-    if (e__ != cudaSuccess) return aadgpu_fail(what, e__); \
+    if (e__ != cudaSuccess) return aadgpu_fail_drained(gpu, what, e__); \
   } while (0)
 
 /* Every entry point that uses a context's streams and scratch buffers runs under that context's lock
@@ -198,6 +213,60 @@ int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes)
   return 1;
 }
 
+/* ---- host link probe ---------------------------------------------------------------------- */
+
+static double wall_seconds(void)
+{
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+/* What this device's host link delivers to plain 1-D copies between pinned host memory and HBM, through the same
+ * streams the pipelines use: host -> device alone, device -> host alone, and both directions at once (GB/s,
+ * aggregate for the last).  bench.py runs it on every rank at the same time, so the end-to-end numbers can be
+ * read against what the box's host side actually gives N devices together (tools/microbench/pcie.cu is the
+ * stand-alone version). */
+static AADApiResult AADGpu_LinkProbe_unlocked(struct AADGpu *gpu, size_t bytes, int repeats, double gbs[3])
+{
+  if (bytes == 0 || repeats <= 0 || gbs == NULL) return AAD_APIRESULT_INVALID_ARGUMENT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  if (!aadgpu_reserve(gpu, &gpu->pcm, bytes)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm2, bytes)) return AAD_APIRESULT_NG;
+  void *up = NULL, *down = NULL;
+  if (cudaMallocHost(&up, bytes) != cudaSuccess || cudaMallocHost(&down, bytes) != cudaSuccess) {
+    if (up) cudaFreeHost(up);
+    return aadgpu_fail("cudaMallocHost (link probe)", cudaGetLastError());
+  }
+  memset(up, 0x5A, bytes);
+  memset(down, 0, bytes);
+  cudaError_t e = cudaSuccess;
+  for (int mode = 0; mode < 3 && e == cudaSuccess; mode++) {
+    double t0 = 0.0;
+    for (int r = -1; r < repeats && e == cudaSuccess; r++) {      /* r == -1: warm-up, not timed */
+      if (mode != 1) e = cudaMemcpyAsync(gpu->pcm.ptr, up, bytes, cudaMemcpyHostToDevice, gpu->s_in);
+      if (e == cudaSuccess && mode != 0) e = cudaMemcpyAsync(down, gpu->pcm2.ptr, bytes, cudaMemcpyDeviceToHost, gpu->s_out);
+      if (r == -1) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_in);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_out);
+        t0 = wall_seconds();
+      }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_in);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_out);
+    gbs[mode] = (double)bytes * repeats * (mode == 2 ? 2.0 : 1.0) / (wall_seconds() - t0) / 1e9;
+  }
+  cudaFreeHost(up);
+  cudaFreeHost(down);
+  if (e != cudaSuccess) return aadgpu_fail_drained(gpu, "link probe", e);
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_LinkProbe(struct AADGpu *gpu, size_t bytes, int repeats, double gbs[3])
+{
+  WITH_CONTEXT_LOCK(gpu, AADGpu_LinkProbe_unlocked(gpu, bytes, repeats, gbs));
+}
+
 /* ---- parameter checks ------------------------------------------------------------------- */
 
 /* The checks AADEncoder_SetEncodeParameter (src/aad_encoder.c:741-770) and
@@ -323,6 +392,9 @@ AADApiResult AADGpu_DecodeBatchDevice(struct AADGpu *gpu, const struct AADGpuBat
   p.block_begin = 0;
   p.block_end = aadf_num_blocks(batch->num_samples, geo.samples_per_block);
   p.read_headers = 1;
+  /* a stream's own header may claim more samples than the batch describes (corrupt or mismatched): the rows
+   * of pcm_dev hold batch->num_samples, and nothing is written past that */
+  p.uniform_samples = batch->num_samples;
   p.pcm = pcm_dev;
   p.pcm_clip_stride = batch->pcm_stream_stride;
   p.pcm_ch_stride = batch->pcm_channel_stride;
@@ -405,6 +477,17 @@ static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
   if (s < 1) s = 1;
   if (s > AADGPU_MAX_SLICES) s = AADGPU_MAX_SLICES;
   if (s > num_blocks) s = num_blocks ? num_blocks : 1;
+  return (uint32_t)s;
+}
+
+/* one stream (or a shard of one): pieces of ~8 MiB so that even an eighth of an hour-long file overlaps its
+ * copies with its kernels; at most AADGPU_MAX_SLICES (one event each), at most `units` */
+static uint32_t pick_stream_slices(uint64_t bytes, uint64_t units)
+{
+  uint64_t s = bytes / ((uint64_t)8 << 20);
+  if (s < 1) s = 1;
+  if (s > AADGPU_MAX_SLICES) s = AADGPU_MAX_SLICES;
+  if (s > units) s = units ? units : 1;
   return (uint32_t)s;
 }
 
@@ -564,6 +647,7 @@ static AADApiResult AADGpu_DecodeBatch_unlocked(struct AADGpu *gpu, const struct
   p.num_streams = N;
   p.geo = geo;
   p.read_headers = 1;
+  p.uniform_samples = ns;
   p.pcm = d_pcm;
   p.pcm_clip_stride = (uint64_t)C * pitch;
   p.pcm_ch_stride = pitch;
@@ -662,6 +746,7 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
   d.num_streams = N;
   d.geo = geo;
   d.read_headers = 1;                                 /* each stream's own length, written by the encoder */
+  d.uniform_samples = ns;                             /* ... and never more than a row holds */
   d.pcm = d_out;
   d.pcm_clip_stride = (uint64_t)C * pitch;
   d.pcm_ch_stride = pitch;
@@ -850,17 +935,29 @@ static AADApiResult encode_wav_device(struct AADGpu *gpu, const struct AADEncode
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
   cudaStream_t s = gpu->s_run;
-  if (interleaved != NULL && wav_bits == 16) {
-    if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * num_samples * 2)) return AAD_APIRESULT_NG;
-    CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved, (size_t)C * num_samples * 2, cudaMemcpyHostToDevice, s), "H2D wav");
-    CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s),
-       "deinterleave kernel launch");
-  } else if (interleaved != NULL) {   /* 8 / 24 / 32-bit chunk: narrowed to its top 16 bits while de-interleaving */
-    const size_t raw_bytes = (size_t)C * num_samples * (wav_bits / 8);
-    if (!aadgpu_reserve(gpu, &gpu->raw, raw_bytes)) return AAD_APIRESULT_NG;
-    CU(cudaMemcpyAsync(gpu->raw.ptr, interleaved, raw_bytes, cudaMemcpyHostToDevice, s), "H2D wav data");
-    CU((cudaError_t)aadk_launch_wav_to_planar16((const uint8_t *)gpu->raw.ptr, wav_bits, (int16_t *)gpu->pcm.ptr, pitch, C,
-                                                num_samples, s), "wav_to_planar16 kernel launch");
+  if (interleaved != NULL) {
+    /* the data chunk goes up in pieces on the copy stream; each piece is narrowed to 16 bits (8 / 24 / 32-bit
+     * chunks: top 16 bits) and de-interleaved on the kernel stream while the next one is on the link */
+    const uint32_t sample_bytes = wav_bits / 8;
+    const size_t raw_bytes = (size_t)C * num_samples * sample_bytes;
+    struct aadgpu_buffer *up = (wav_bits == 16) ? &gpu->wav : &gpu->raw;
+    if (!aadgpu_reserve(gpu, up, raw_bytes)) return AAD_APIRESULT_NG;
+    const uint32_t pieces = pick_stream_slices(raw_bytes, num_samples);
+    for (uint32_t k = 0; k < pieces; k++) {
+      const uint64_t a = (uint64_t)num_samples * k / pieces, b = (uint64_t)num_samples * (k + 1) / pieces;
+      if (b == a) continue;
+      const size_t off = (size_t)a * C * sample_bytes;
+      CU(cudaMemcpyAsync((uint8_t *)up->ptr + off, (const uint8_t *)interleaved + off, (size_t)(b - a) * C * sample_bytes,
+                         cudaMemcpyHostToDevice, gpu->s_in), "H2D wav data");
+      CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+      CU(cudaStreamWaitEvent(s, gpu->ev_in[k], 0), "wait");
+      if (wav_bits == 16)
+        CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)up->ptr + a * C, (int16_t *)gpu->pcm.ptr + a, pitch, C,
+                                                   (uint32_t)(b - a), s), "deinterleave kernel launch");
+      else
+        CU((cudaError_t)aadk_launch_wav_to_planar16((const uint8_t *)up->ptr + off, wav_bits, (int16_t *)gpu->pcm.ptr + a, pitch, C,
+                                                    (uint32_t)(b - a), s), "wav_to_planar16 kernel launch");
+    }
   }
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)bound + 128, s), "memset aad");
   struct aadk_encode_params p;
@@ -942,40 +1039,66 @@ AADApiResult AADGpu_EncodeWav(struct AADGpu *gpu, const struct AADEncodeParamete
   WITH_CONTEXT_LOCK(gpu, AADGpu_EncodeWav_unlocked(gpu, prm, wav_data, wav_bits_per_sample, num_samples, data, data_size, output_size));
 }
 
-/* decode the stream at d_aad (device) into gpu->pcm (planar) and gpu->wav (interleaved) */
+static void geometry_of_header(const struct AADHeaderInfo *h, struct aadf_geometry *geo)
+{
+  geo->channels = h->num_channels;
+  geo->bits = h->bits_per_sample;
+  geo->block_size = h->block_size;
+  geo->samples_per_block = h->num_samples_per_block;
+  geo->ms = (h->ch_process_method == AAD_CH_PROCESS_METHOD_MS) ? 1u : 0u;
+}
+
+/* Blocks [b0, b1) of the stream whose byte `byte_base` lies at d_aad, into WAV order at d_wav (frame
+ * `sample_base` first).  The decoder's flush writes the frames itself where the shape allows (mono, 2 / 4 / 8
+ * channels on the staged kernels); otherwise the planes go to gpu->pcm and one more pass interleaves them. */
+static AADApiResult launch_decode_wav_order(struct AADGpu *gpu, const struct aadf_geometry *geo, const uint8_t *d_aad,
+                                            uint64_t byte_base, uint64_t valid_size, uint32_t num_samples, uint32_t b0,
+                                            uint32_t b1, int16_t *d_wav, uint64_t sample_base, uint64_t shard_samples,
+                                            cudaStream_t s)
+{
+  const uint32_t C = geo->channels, spb = geo->samples_per_block;
+  struct aadk_decode_params p;
+  memset(&p, 0, sizeof(p));
+  p.aad = d_aad;
+  p.aad_stride = 0;
+  p.uniform_size = (uint32_t)valid_size;
+  p.num_streams = 1;
+  p.geo = *geo;
+  p.block_begin = b0;
+  p.block_end = b1;
+  p.uniform_samples = num_samples;
+  p.byte_base = byte_base;
+  p.sample_base = sample_base;
+  p.pcm = d_wav;
+  p.interleaved = 1;
+  if (aadk_decode_interleaved_ok(&p)) {
+    CU((cudaError_t)aadk_launch_decode(&p, s), "decode kernel launch");
+    return AAD_APIRESULT_OK;
+  }
+  const uint64_t pitch = round_up64(shard_samples, 64);
+  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
+  p.interleaved = 0;
+  p.pcm = gpu->pcm.ptr;
+  p.pcm_ch_stride = pitch;
+  CU((cudaError_t)aadk_launch_decode(&p, s), "decode kernel launch");
+  const uint64_t f0 = (uint64_t)b0 * spb - sample_base;
+  const uint64_t f1 = ((uint64_t)b1 * spb < num_samples ? (uint64_t)b1 * spb : num_samples) - sample_base;
+  if (f1 > f0)
+    CU((cudaError_t)aadk_launch_interleave16((const int16_t *)gpu->pcm.ptr + f0, pitch, d_wav + f0 * C, C, (uint32_t)(f1 - f0), s),
+       "interleave kernel launch");
+  return AAD_APIRESULT_OK;
+}
+
+/* decode the complete stream at d_aad (device, just encoded there) into gpu->wav in WAV order */
 static AADApiResult decode_to_interleaved_device(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *d_aad,
                                                  uint64_t aad_bytes)
 {
   struct aadf_geometry geo;
-  geo.channels = h->num_channels;
-  geo.bits = h->bits_per_sample;
-  geo.block_size = h->block_size;
-  geo.samples_per_block = h->num_samples_per_block;
-  geo.ms = (h->ch_process_method == AAD_CH_PROCESS_METHOD_MS) ? 1u : 0u;
+  geometry_of_header(h, &geo);
   const uint32_t C = geo.channels, ns = h->num_samples;
-  const uint64_t pitch = round_up64(ns, 64);
-  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * ns * 2)) return AAD_APIRESULT_NG;
-  cudaStream_t s = gpu->s_run;
-  /* samples of blocks the data does not reach stay zero (the reference leaves them untouched) */
-  CU(cudaMemsetAsync(gpu->pcm.ptr, 0, (size_t)C * pitch * 2, s), "memset pcm");
-  struct aadk_decode_params p;
-  memset(&p, 0, sizeof(p));
-  p.aad = d_aad;
-  p.aad_stride = aad_bytes;
-  p.uniform_size = (uint32_t)aad_bytes;
-  p.num_streams = 1;
-  p.geo = geo;
-  p.block_begin = 0;
-  p.block_end = aadf_num_blocks(ns, geo.samples_per_block);
-  p.uniform_samples = ns;
-  p.pcm = gpu->pcm.ptr;
-  p.pcm_clip_stride = (uint64_t)C * pitch;
-  p.pcm_ch_stride = pitch;
-  CU((cudaError_t)aadk_launch_decode(&p, s), "decode kernel launch");
-  CU((cudaError_t)aadk_launch_interleave16((const int16_t *)gpu->pcm.ptr, pitch, (int16_t *)gpu->wav.ptr, C, ns, s),
-     "interleave kernel launch");
-  return AAD_APIRESULT_OK;
+  return launch_decode_wav_order(gpu, &geo, d_aad, 0, aad_bytes, ns, 0, aadf_num_blocks(ns, geo.samples_per_block),
+                                 (int16_t *)gpu->wav.ptr, 0, ns, gpu->s_run);
 }
 
 /* the checks of AADDecoder_DecodeHeader + CheckHeaderFormat (src/aad_decoder.c:99-225), via the drop-in entry */
@@ -986,6 +1109,36 @@ static AADApiResult parse_stream_header(const uint8_t *data, uint32_t data_size,
   return aaddec_check_header(h);
 }
 
+/* The block loop of AADDecoder_DecodeWhole (src/aad_decoder.c:514-534): block b is visited while b * spb <
+ * num_samples and its first byte exists; a last block too short for its channel headers ends the loop with
+ * AAD_APIRESULT_INSUFFICIENT_DATA (*tail) after the earlier blocks were decoded.  Returns the blocks to decode. */
+static uint32_t stream_block_span(const struct AADHeaderInfo *h, uint32_t data_size, AADApiResult *tail)
+{
+  const uint32_t by_samples = aadf_num_blocks(h->num_samples, h->num_samples_per_block);
+  const uint64_t payload = (uint64_t)data_size - AADF_FILE_HEADER_BYTES;
+  const uint64_t by_bytes = (payload + h->block_size - 1) / h->block_size;
+  uint32_t blocks = (uint32_t)(by_bytes < by_samples ? by_bytes : by_samples);
+  *tail = AAD_APIRESULT_OK;
+  if (blocks > 0) {
+    const uint64_t last_avail = payload - (uint64_t)(blocks - 1) * h->block_size;
+    if (last_avail < (uint64_t)AADF_CHANNEL_HEADER_BYTES * h->num_channels) {
+      blocks--;
+      *tail = AAD_APIRESULT_INSUFFICIENT_DATA;
+    }
+  }
+  return blocks;
+}
+
+/* samples (per channel) that `blocks` leading blocks deliver */
+static uint64_t stream_decoded_samples(const struct AADHeaderInfo *h, uint32_t blocks)
+{
+  const uint64_t n = (uint64_t)blocks * h->num_samples_per_block;
+  return n < h->num_samples ? n : h->num_samples;
+}
+
+static AADApiResult decode_stream_range_unlocked(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
+                                        uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved);
+
 static AADApiResult AADGpu_DecodeInterleaved16_unlocked(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
                                         int16_t *interleaved, uint32_t capacity_samples)
 {
@@ -994,18 +1147,14 @@ static AADApiResult AADGpu_DecodeInterleaved16_unlocked(struct AADGpu *gpu, cons
   const AADApiResult r = parse_stream_header(data, data_size, &h);
   if (r != AAD_APIRESULT_OK) return r;
   if (capacity_samples < h.num_samples) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
-  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
-  uint64_t span = aadf_stream_bytes_bound(h.num_samples, h.block_size, h.num_samples_per_block);
-  if (span > data_size) span = data_size;
-  if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 128)) return AAD_APIRESULT_NG;
-  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
-  CU(cudaMemcpyAsync(d_aad, data, (size_t)span, cudaMemcpyHostToDevice, gpu->s_run), "H2D aad");
-  const AADApiResult e = decode_to_interleaved_device(gpu, &h, d_aad, span);
-  if (e != AAD_APIRESULT_OK) return e;
-  CU(cudaMemcpyAsync(interleaved, gpu->wav.ptr, (size_t)h.num_channels * h.num_samples * 2, cudaMemcpyDeviceToHost, gpu->s_run),
-     "D2H wav");
-  CU(cudaStreamSynchronize(gpu->s_run), "sync");
-  return AAD_APIRESULT_OK;
+  AADApiResult tail;
+  const uint32_t blocks = stream_block_span(&h, data_size, &tail);
+  /* samples of blocks the data does not reach are zero (the reference leaves them untouched) */
+  const uint64_t decoded = stream_decoded_samples(&h, blocks);
+  if (decoded < h.num_samples)
+    memset(interleaved + decoded * h.num_channels, 0, (size_t)(h.num_samples - decoded) * h.num_channels * 2);
+  const AADApiResult e = decode_stream_range_unlocked(gpu, &h, data, data_size, 0, blocks, interleaved);
+  return (e != AAD_APIRESULT_OK) ? e : tail;
 }
 
 AADApiResult AADGpu_DecodeInterleaved16(struct AADGpu *gpu, const uint8_t *data, uint32_t data_size,
@@ -1313,52 +1462,48 @@ AADApiResult AADGpuGroup_DecodeBatch(struct AADGpuGroup *g, const struct AADGpuB
   return group_run(tasks, n);
 }
 
-/* blocks [b0, b1) of one stream -> interleaved samples [b0*spb, min(b1*spb, ns)) of the caller's buffer */
+/* Blocks [b0, b1) of one stream -> interleaved samples [b0*spb, min(b1*spb, ns)) of the caller's buffer; every
+ * block of the range has its channel headers (stream_block_span).  The device holds only the range's own bytes and
+ * samples.  Sliced by block range over three streams: while slice k decodes, slice k+1's bytes come up and slice
+ * k-1's frames go down; the decoder writes WAV order itself, so the samples cross HBM once. */
 static AADApiResult decode_stream_range_unlocked(struct AADGpu *gpu, const struct AADHeaderInfo *h, const uint8_t *data,
                                         uint32_t data_size, uint32_t b0, uint32_t b1, int16_t *interleaved)
 {
-  const uint32_t C = h->num_channels, spb = h->num_samples_per_block, bs = h->block_size, ns = h->num_samples;
+  struct aadf_geometry geo;
+  geometry_of_header(h, &geo);
+  const uint32_t C = geo.channels, spb = geo.samples_per_block, bs = geo.block_size, ns = h->num_samples;
   const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < ns) ? (uint64_t)b1 * spb : ns;
   if (b1 <= b0 || s1 <= s0) return AAD_APIRESULT_OK;
   CU(cudaSetDevice(gpu->device), "cudaSetDevice");
   const uint64_t count = s1 - s0;
-  const uint64_t pitch = round_up64(count, 64);
   const uint64_t byte0 = AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
   uint64_t byte1 = AADF_FILE_HEADER_BYTES + (uint64_t)b1 * bs;
   if (byte1 > data_size) byte1 = data_size;
   const uint64_t span = byte1 > byte0 ? byte1 - byte0 : 0;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 256)) return AAD_APIRESULT_NG;
-  if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * count * 2)) return AAD_APIRESULT_NG;
-  cudaStream_t s = gpu->s_run;
   uint8_t *d_shard = (uint8_t *)gpu->aad.ptr;       /* block b0 at the (256-byte aligned) start */
-  if (span) CU(cudaMemcpyAsync(d_shard, data + byte0, (size_t)span, cudaMemcpyHostToDevice, s), "H2D aad shard");
-  CU(cudaMemsetAsync(gpu->pcm.ptr, 0, (size_t)C * pitch * 2, s), "memset pcm");
-  struct aadk_decode_params p;
-  memset(&p, 0, sizeof(p));
-  /* the kernels address block b at aad + 31 + b*block_size and sample b*spb of a row at pcm + b*spb:
-   * shift both bases back so the shard's first block and sample land at the buffers' starts (the
-   * shifted pointers are only ever dereferenced inside the shard) */
-  p.aad = d_shard - byte0;
-  p.aad_stride = 0;
-  p.uniform_size = (uint32_t)byte1;
-  p.num_streams = 1;
-  p.geo.channels = C;
-  p.geo.bits = h->bits_per_sample;
-  p.geo.block_size = bs;
-  p.geo.samples_per_block = spb;
-  p.geo.ms = (h->ch_process_method == AAD_CH_PROCESS_METHOD_MS) ? 1u : 0u;
-  p.block_begin = b0;
-  p.block_end = b1;
-  p.uniform_samples = ns;
-  p.pcm = (int16_t *)gpu->pcm.ptr - s0;
-  p.pcm_clip_stride = 0;
-  p.pcm_ch_stride = pitch;
-  CU((cudaError_t)aadk_launch_decode(&p, s), "decode kernel launch");
-  CU((cudaError_t)aadk_launch_interleave16((const int16_t *)gpu->pcm.ptr, pitch, (int16_t *)gpu->wav.ptr, C, (uint32_t)count, s),
-     "interleave kernel launch");
-  CU(cudaMemcpyAsync(interleaved + s0 * C, gpu->wav.ptr, (size_t)C * count * 2, cudaMemcpyDeviceToHost, s), "D2H wav shard");
-  CU(cudaStreamSynchronize(s), "sync");
+  int16_t *d_wav = (int16_t *)gpu->wav.ptr;
+  const uint32_t slices = pick_stream_slices(count * C * 2, b1 - b0);
+  for (uint32_t k = 0; k < slices; k++) {
+    const uint32_t k0 = b0 + (uint32_t)((uint64_t)(b1 - b0) * k / slices), k1 = b0 + (uint32_t)((uint64_t)(b1 - b0) * (k + 1) / slices);
+    const uint64_t f0 = (uint64_t)k0 * spb, f1 = ((uint64_t)k1 * spb < s1) ? (uint64_t)k1 * spb : s1;
+    const uint64_t o0 = AADF_FILE_HEADER_BYTES + (uint64_t)k0 * bs;
+    uint64_t o1 = AADF_FILE_HEADER_BYTES + (uint64_t)k1 * bs;
+    if (o1 > byte1) o1 = byte1;
+    if (o1 > o0)
+      CU(cudaMemcpyAsync(d_shard + (o0 - byte0), data + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, gpu->s_in), "H2D aad slice");
+    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
+    const AADApiResult e = launch_decode_wav_order(gpu, &geo, d_shard, byte0, byte1, ns, k0, k1, d_wav, s0, count, gpu->s_run);
+    if (e != AAD_APIRESULT_OK) return e;
+    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
+    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    if (f1 > f0)
+      CU(cudaMemcpyAsync(interleaved + f0 * C, d_wav + (f0 - s0) * C, (size_t)(f1 - f0) * C * 2, cudaMemcpyDeviceToHost, gpu->s_out),
+         "D2H wav slice");
+  }
+  CU(cudaStreamSynchronize(gpu->s_out), "sync");
   return AAD_APIRESULT_OK;
 }
 
@@ -1377,12 +1522,9 @@ AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_
   if (r != AAD_APIRESULT_OK) return r;
   if (capacity_samples < h.num_samples) return AAD_APIRESULT_INSUFFICIENT_BUFFER;
   /* blocks the data reaches (src/aad_decoder.c:514-534); samples of later blocks are zero */
-  const uint32_t by_samples = aadf_num_blocks(h.num_samples, h.num_samples_per_block);
-  const uint64_t payload = (uint64_t)data_size - AADF_FILE_HEADER_BYTES;
-  const uint64_t by_bytes = (payload + h.block_size - 1) / h.block_size;
-  const uint32_t blocks = (uint32_t)(by_bytes < by_samples ? by_bytes : by_samples);
-  const uint64_t decoded = ((uint64_t)blocks * h.num_samples_per_block < h.num_samples)
-                               ? (uint64_t)blocks * h.num_samples_per_block : h.num_samples;
+  AADApiResult tail;
+  const uint32_t blocks = stream_block_span(&h, data_size, &tail);
+  const uint64_t decoded = stream_decoded_samples(&h, blocks);
   if (decoded < h.num_samples)
     memset(interleaved + decoded * h.num_channels, 0, (size_t)(h.num_samples - decoded) * h.num_channels * 2);
   struct group_task tasks[AADGPU_MAX_GROUP];
@@ -1402,7 +1544,8 @@ AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_
     t->block_end = (uint32_t)b1;
     t->pcm_out = interleaved;
   }
-  return n ? group_run(tasks, n) : AAD_APIRESULT_OK;
+  const AADApiResult e = n ? group_run(tasks, n) : AAD_APIRESULT_OK;
+  return (e != AAD_APIRESULT_OK) ? e : tail;
 }
 
 /* ---- one stream ENCODED by a group: segment mode only ------------------------------------------- */
@@ -1433,17 +1576,27 @@ static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struc
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + (size_t)bs + 256)) return AAD_APIRESULT_NG;
   cudaStream_t s = gpu->s_run;
-  CU(cudaMemcpyAsync(gpu->wav.ptr, interleaved + s0 * C, (size_t)C * count * 2, cudaMemcpyHostToDevice, s), "H2D wav shard");
-  CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr, (int16_t *)gpu->pcm.ptr, pitch, C, (uint32_t)count, s),
-     "deinterleave kernel launch");
+  /* the shard's samples come up in pieces, each de-interleaved while the next is on the link */
+  const uint32_t pieces = pick_stream_slices(count * C * 2, count);
+  for (uint32_t k = 0; k < pieces; k++) {
+    const uint64_t a = count * k / pieces, b = count * (k + 1) / pieces;
+    if (b == a) continue;
+    CU(cudaMemcpyAsync((int16_t *)gpu->wav.ptr + a * C, interleaved + (s0 + a) * C, (size_t)(b - a) * C * 2, cudaMemcpyHostToDevice,
+                       gpu->s_in), "H2D wav shard");
+    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(s, gpu->ev_in[k], 0), "wait");
+    CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr + a * C, (int16_t *)gpu->pcm.ptr + a, pitch, C,
+                                               (uint32_t)(b - a), s), "deinterleave kernel launch");
+  }
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)span + (size_t)bs + 256, s), "memset aad");
-  /* the shard's first block 32-byte aligned at ptr + 32, the file header (shard 0 only) right in front of it;
-   * the kernel addresses block b at aad + 31 + b*block_size and sample i of a row at pcm + i, so both bases are
-   * shifted back to absolute indexing (only ever dereferenced inside the shard) */
+  /* the shard's first block 32-byte aligned at ptr + 32, the file header (shard 0 only) right in front of it; the
+   * kernel is told which byte of the stream and which sample of the rows its buffers start at */
   uint8_t *d_block0 = (uint8_t *)gpu->aad.ptr + 32;
+  const uint64_t lead = (b0 == 0) ? AADF_FILE_HEADER_BYTES : 0;
   struct aadk_encode_params p;
   memset(&p, 0, sizeof(p));
-  p.pcm = (const int16_t *)gpu->pcm.ptr - s0;
+  p.pcm = (const int16_t *)gpu->pcm.ptr;
+  p.sample_base = s0;
   p.pcm_clip_stride = 0;
   p.pcm_ch_stride = pitch;
   p.uniform_samples = ns;
@@ -1451,14 +1604,14 @@ static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struc
   p.geo = geo;
   p.sampling_rate = prm->sampling_rate;
   p.trials = prm->num_encode_trials;
-  p.aad = d_block0 - byte0;
+  p.aad = d_block0 - lead;
+  p.byte_base = byte0 - lead;
   p.aad_stride = 0;
   p.block_begin = b0;
   p.block_end = b1;
   p.segment_blocks = segment_blocks;
   p.num_segments = (nblk + segment_blocks - 1) / segment_blocks;
   CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
-  const uint64_t lead = (b0 == 0) ? AADF_FILE_HEADER_BYTES : 0;
   CU(cudaMemcpyAsync(data + byte0 - lead, d_block0 - lead, (size_t)(span + lead), cudaMemcpyDeviceToHost, s), "D2H aad shard");
   CU(cudaStreamSynchronize(s), "sync");
   return AAD_APIRESULT_OK;

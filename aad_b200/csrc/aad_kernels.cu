@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "aad_format.h"
 #include "aad_kernels.h"
 #include "aad_tables_data.h"
@@ -25,15 +27,24 @@ __device__ const int16_t g_delta2[2] = AADK_DELTA2_INIT;
 __device__ const int16_t g_delta3[4] = AADK_DELTA3_INIT;
 __device__ const int16_t g_delta4[8] = AADK_DELTA4_INIT;
 
-unsigned long long g_launches = 0;
-int g_force_generic = 0;   /* tests: route everything through the generic kernels */
-int g_dec_wide_all = 0;    /* tests: mono / stereo decode through the any-channel-count staged kernel too */
-int g_enc_pairing = 1;     /* tests / measurement: 0 = never pair the independent dry passes */
+/* process-wide counters and test switches: contexts on different host threads launch concurrently */
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_force_generic{0};   /* tests: route everything through the generic kernels */
+std::atomic<int> g_dec_wide_all{0};    /* tests: mono / stereo decode through the any-channel-count staged kernel too */
+std::atomic<int> g_enc_pairing{1};     /* tests / measurement: 0 = never pair the independent dry passes */
 
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 __device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 __device__ __forceinline__ int32_t clamp16(int32_t v) { return max(-32768, min(32767, v)); }
+
+/* read_headers: a stream's sample count comes from its own 31-byte header, but never exceeds what the launch says a
+ * row holds (cap != 0): a corrupt or mismatched header must not write past the rows the caller described */
+__device__ __forceinline__ uint32_t dec_header_samples(const uint8_t *slot, uint32_t size, uint32_t cap)
+{
+  const uint32_t n = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  return (cap != 0u && n > cap) ? cap : n;
+}
 
 /* Tables staged in shared memory: the step lookup is lane-divergent, which would serialise
  * on the constant cache. */
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
   const uint8_t *slot = p.aad + stream * p.aad_stride;
   const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
   uint32_t ns = p.uniform_samples;
-  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  if (p.read_headers) ns = dec_header_samples(slot, size, p.uniform_samples);
   if ((uint64_t)b * spb >= ns) return;
   const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
   /* a block whose channel headers are not all present is not decoded (src/aad_decoder.c:347) */
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
   if ((uint64_t)b * spb >= buf) return;   /* nothing of this block fits the output buffer */
   const uint32_t want = min(spb, buf - b * spb);
 
-  const uint8_t *blk = slot + blk_off;
+  const uint8_t *blk = slot + (blk_off - p.byte_base);   /* p.aad points at byte byte_base of the stream */
   auto rd = [&](uint32_t pos) -> uint32_t { return pos < avail ? (uint32_t)blk[pos] : 0u; };
 
   Chain c;
@@ -166,6 +177,7 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
     const uint32_t hp = ch * AADF_CHANNEL_HEADER_BYTES;
     const uint32_t head = (rd(hp) << 8) | rd(hp + 1);
     c.idx = (int32_t)(int16_t)(head >> 4);
+    c.idx = max(0, min(c.idx, AADF_INDEX_MAX));    /* a corrupt header must not index outside the table */
     const uint32_t shift = head & 0xFu;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(128) aad_decode_generic(const aadk_decode_para
     }
   }
 
-  const uint64_t out_base = stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + (uint64_t)b * spb;
+  const uint64_t out_base = stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + ((uint64_t)b * spb - p.sample_base);
   int16_t *out16 = (int16_t *)p.pcm + out_base;
   auto put = [&](uint32_t i, int32_t v) {
     if (i < want) out16[i] = (int16_t)v;
@@ -213,13 +225,13 @@ __global__ void aad_ms_to_lr(const aadk_decode_params p)
   const uint8_t *slot = p.aad + stream * p.aad_stride;
   const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
   uint32_t ns = p.uniform_samples;
-  if (p.read_headers) ns = (size >= AADF_FILE_HEADER_BYTES) ? aadf_get_be32(slot + 14) : 0u;
+  if (p.read_headers) ns = dec_header_samples(slot, size, p.uniform_samples);
   if ((uint64_t)b * spb >= ns) return;
   const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * p.geo.block_size;
   if (blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C > size) return;
   const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
   if (s >= buf) return;
-  const uint64_t i0 = stream * p.pcm_clip_stride + s;
+  const uint64_t i0 = stream * p.pcm_clip_stride + (s - p.sample_base);
   const uint64_t i1 = i0 + p.pcm_ch_stride;
   int16_t *o = (int16_t *)p.pcm;
   const int32_t m = o[i0], d = o[i1];
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
   const uint32_t ns = p.num_samples ? p.num_samples[stream] : p.uniform_samples;
 
   uint8_t *out = p.aad + stream * p.aad_stride;
-  if (ch == 0 && seg == 0 && p.block_begin == 0) {
+  if (ch == 0 && seg == 0 && p.block_begin == 0 && p.byte_base == 0) {
     if (ns > 0) aadf_write_file_header(out, C, ns, p.sampling_rate, BITS, bs, spb, p.geo.ms);
     if (p.out_sizes) p.out_sizes[stream] = ns ? (uint32_t)aadf_stream_bytes(ns, C, BITS, bs, spb) : 0u;
   }
@@ -313,16 +325,17 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
 
   const uint32_t seg_first = p.segment_blocks ? seg * p.segment_blocks : 0u;
   const uint32_t seg_end = p.segment_blocks ? seg_first + p.segment_blocks : 0xFFFFFFFFu;
-  const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), p.block_end), seg_end);
-  const uint32_t b_begin = max(p.block_begin, seg_first);
+  const uint32_t rel = (p.segment_blocks && p.segment_relative) ? seg_first : 0u;   /* aad_kernels.h: segment_relative */
+  const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), (uint32_t)min((uint64_t)rel + p.block_end, (uint64_t)0xFFFFFFFFu)), seg_end);
+  const uint32_t b_begin = max(rel + p.block_begin, seg_first);
   if (p.segment_blocks && b_begin == seg_first) {
 #pragma unroll
     for (int k = 0; k < 4; k++) c.w[k] = 0;
     c.idx = 0;
   }
   for (uint32_t b = b_begin; b < nblk; b++) {
-    const uint32_t first = b * spb;
-    const uint32_t n = min(spb, ns - first);
+    const uint32_t n = min(spb, ns - b * spb);
+    const uint32_t first = b * spb - (uint32_t)p.sample_base;   /* the rows of p.pcm start at sample sample_base */
     const uint32_t limit = first + n;
 
     if (p.trials > 0) {   /* src/aad_encoder.c:470-562 */
@@ -348,7 +361,7 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
     const int32_t keep = (int32_t)~((1u << shift) - 1u);
 #pragma unroll
     for (int k = 0; k < 4; k++) c.w[k] &= keep;
-    uint8_t *blk = out + AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+    uint8_t *blk = out + (AADF_FILE_HEADER_BYTES + (uint64_t)b * bs - p.byte_base);
     uint8_t *hp = blk + ch * AADF_CHANNEL_HEADER_BYTES;
     aadf_put_be16(hp, (((uint32_t)c.idx << 4) | (shift & 0xFu)) & 0xFFFFu);
 #pragma unroll
@@ -550,10 +563,23 @@ uint64_t aadk_launch_count(void) { return g_launches; }
 void aadk_force_generic(int on) { g_force_generic = (on == 1); g_dec_wide_all = (on == 2); }
 void aadk_set_encoder_pairing(int on) { g_enc_pairing = on ? 1 : 0; }
 
+int aadk_decode_interleaved_ok(const struct aadk_decode_params *p)
+{
+  struct aadk_decode_params q = *p;
+  q.interleaved = 1;
+  const uint32_t C = q.geo.channels;
+  if (C == 1) return 1;                                /* one channel: WAV order is the plane itself */
+  if (g_force_generic || !dec_fast_eligible(q)) return 0;
+  if (C == 2) return 1;                                /* aad_decode_fast<BITS, 2, 1>, mid/side included */
+  return (C == 4 || C == 8) && !q.geo.ms;              /* aad_decode_wide; mid/side there is a pass over planes */
+}
+
 int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
 {
   cudaStream_t s = (cudaStream_t)stream;
   if (p->block_end <= p->block_begin) return 0;
+  if (p->interleaved && !aadk_decode_interleaved_ok(p)) return (int)cudaErrorInvalidValue;
+  if (p->read_headers && p->byte_base != 0) return (int)cudaErrorInvalidValue;
   const uint64_t threads = (uint64_t)p->num_streams * (p->block_end - p->block_begin) * p->geo.channels;
   if (threads == 0) return 0;
   if (dec_fast_eligible(*p) && !g_force_generic) {
@@ -576,7 +602,7 @@ int aadk_launch_decode(const struct aadk_decode_params *p, void *stream)
   }
   g_launches++;
   /* mid/side -> left/right: inside aad_decode_fast's flush for stereo, a pass of its own after the other kernels */
-  const bool fused_ms = dec_fast_eligible(*p) && !g_force_generic && p->geo.channels == 2 && !g_dec_wide_all;
+  const bool fused_ms = dec_fast_eligible(*p) && !g_force_generic && p->geo.channels == 2 && (!g_dec_wide_all || p->interleaved);
   if (p->geo.ms && p->geo.channels >= 2 && !fused_ms) {
     const uint64_t n = (uint64_t)p->num_streams * (p->block_end - p->block_begin) * p->geo.samples_per_block;
     aad_ms_to_lr<<<grid_for(n, 256), 256, 0, s>>>(*p);

@@ -27,13 +27,26 @@ struct aadk_decode_params {
   struct aadf_geometry geo;
   uint32_t block_begin;        /* blocks [block_begin, block_end) of every stream are decoded */
   uint32_t block_end;
-  uint32_t uniform_samples;    /* samples per channel when read_headers == 0 */
+  uint32_t uniform_samples;    /* samples per channel when read_headers == 0; with read_headers: cap on what a header may claim (0 = none) */
   uint32_t read_headers;       /* 1: take num_samples from each stream's own 31-byte header */
   uint32_t buf_samples;        /* output capacity per channel (reference DecodeWhole semantics); 0 = num_samples */
   void *pcm;                   /* planar int16: sample s of channel c of stream i at i*clip_stride + c*ch_stride + s */
   uint64_t pcm_clip_stride;    /* in samples */
   uint64_t pcm_ch_stride;      /* in samples */
+  /* Shards of one stream (a device holds only its own byte / sample range): `aad` points at byte byte_base of
+   * every stream and the rows of `pcm` start at sample sample_base.  Sizes, block and sample numbers stay
+   * absolute; the kernels subtract the bases when they form addresses, so no pointer ever lies outside its
+   * allocation.  read_headers needs byte_base == 0. */
+  uint64_t byte_base;
+  uint64_t sample_base;
+  /* 1: WAV order -- sample s of channel c of stream i at i*clip_stride + (s - sample_base)*channels + c
+   * (pcm_ch_stride unused); only where aadk_decode_interleaved_ok() says so */
+  uint32_t interleaved;
 };
+
+/* 1 when aadk_launch_decode can write WAV-order output itself for this shape (mono: the same thing;
+ * 2 / 4 / 8 channels on the staged kernels); otherwise decode planar and run aadk_launch_interleave16 */
+int aadk_decode_interleaved_ok(const struct aadk_decode_params *p);
 
 struct aadk_encode_params {
   const void *pcm;             /* planar int16, same addressing as the decoder's output */
@@ -60,6 +73,14 @@ struct aadk_encode_params {
    * shares them. */
   uint32_t segment_blocks;
   uint32_t num_segments;       /* >= 1 when segment_blocks != 0 */
+  /* segment mode only, 1: block_begin / block_end count from the first block of EVERY segment (blocks
+   * [block_begin, block_end) of each segment are encoded), so a host pipeline can cut a stream of many short
+   * chains into slices that keep every chain busy */
+  uint32_t segment_relative;
+  /* shards of one stream: `aad` points at byte byte_base of every stream, the rows of `pcm` start at sample
+   * sample_base (see aadk_decode_params) */
+  uint64_t byte_base;
+  uint64_t sample_base;
 };
 
 int aadk_launch_decode(const struct aadk_decode_params *p, void *stream);

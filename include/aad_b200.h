@@ -78,6 +78,12 @@ uint32_t AADGpu_GetEncodeSegmentBlocks(const struct AADGpu *gpu);
  * (nothing changed).  The device-group calls do this for their own worker threads. */
 int AADGpu_BindHostThread(struct AADGpu *gpu);
 
+/* Measure this device's host link with plain 1-D copies of `bytes` between pinned host memory and HBM, `repeats`
+ * times each: gbs[0] = host -> device alone, gbs[1] = device -> host alone, gbs[2] = both directions at once
+ * (aggregate), in GB/s.  What the pipelined entry points below can at best reach; bench.py reports it beside
+ * their end-to-end figures. */
+AADApiResult AADGpu_LinkProbe(struct AADGpu *gpu, size_t bytes, int repeats, double gbs[3]);
+
 /* pinned host memory for the host entry points (plain malloc'd memory works too, slower) */
 void *AADGpu_HostAlloc(size_t bytes);
 void  AADGpu_HostFree(void *p);

@@ -65,7 +65,8 @@ def test_group_batches_equal_single_device(product, gpu_ctx, bits, channels, ms)
 
 
 @pytest.mark.parametrize("bits,channels,ms,block", [(4, 2, False, 1024), (3, 2, True, 1024), (3, 1, False, 1024),
-                                                    (2, 1, False, 333), (3, 8, False, 1024)])
+                                                    (2, 1, False, 333), (3, 8, False, 1024), (4, 4, False, 1024),
+                                                    (2, 5, True, 1024)])
 def test_one_stream_decodes_in_block_range_shards(product, oracle, bits, channels, ms, block):
     """Every block header reloads the chain state (src/aad_decoder.c:364-380): shards by block range,
     interleaved output, against the oracle's whole-stream decode.  Also a stream with fewer blocks
@@ -77,14 +78,14 @@ def test_one_stream_decodes_in_block_range_shards(product, oracle, bits, channel
         assert rc == 0
         for cut in (len(data), len(data) - (len(data) - 31) // 3):
             blob = np.frombuffer(data[:cut], dtype=np.uint8).copy()
-            rc, want, _ = oracle.decode(data[:cut], fill=0)
-            assert rc in (0, 4)                      # 4 = INSUFFICIENT_DATA when the last block lost its header
+            want_rc, want, _ = oracle.decode(data[:cut], fill=0)
+            assert want_rc in (0, 4)                 # 4 = INSUFFICIENT_DATA when the last block lost its header
             for devices in device_sets(gpu):
                 g = make_group(gpu, devices)
                 try:
                     out = np.full((n, channels), 12345, dtype=np.int16)
                     rc = gpu.lib.AADGpuGroup_DecodeInterleaved16(g, blob.ctypes.data, len(blob), out.ctypes.data, n)
-                    assert rc == 0, gpu.last_error()
+                    assert rc == want_rc, gpu.last_error()   # the earlier blocks are decoded either way (src/aad_decoder.c:522-527)
                     assert np.array_equal(out.T, want), (n, cut, devices)
                 finally:
                     gpu.lib.AADGpuGroup_Destroy(g)
