@@ -683,15 +683,4 @@ int enc_fast_launch_as(const aadk_encode_params &p, cudaStream_t s)
   return (int)cudaGetLastError();
 }
 
-template <int BITS>
-int enc_fast_launch(const aadk_encode_params &p, cudaStream_t s)
-{
-  /* up to one warp per scheduler (148 SMs x 4): pair the independent dry passes inside each thread */
-  const uint64_t chains = (uint64_t)p.num_streams * p.geo.channels * (p.segment_blocks ? p.num_segments : 1u);
-  const bool pair = p.trials >= 1 && chains <= 148ull * 4 * 32 && g_enc_pairing != 0;
-  const bool ms = p.geo.ms && p.geo.channels >= 2;
-  if (pair) return ms ? enc_fast_launch_as<BITS, 1, 1>(p, s) : enc_fast_launch_as<BITS, 0, 1>(p, s);
-  return ms ? enc_fast_launch_as<BITS, 1, 0>(p, s) : enc_fast_launch_as<BITS, 0, 0>(p, s);
-}
-
 }  // namespace

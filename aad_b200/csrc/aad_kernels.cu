@@ -31,7 +31,7 @@ __device__ const int16_t g_delta4[8] = AADK_DELTA4_INIT;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_generic{0};   /* tests: route everything through the generic kernels */
 std::atomic<int> g_dec_wide_all{0};    /* tests: mono / stereo decode through the any-channel-count staged kernel too */
-std::atomic<int> g_enc_pairing{1};     /* tests / measurement: 0 = never pair the independent dry passes */
+std::atomic<int> g_enc_schedule{1};    /* tests / measurement: the encoder's pass schedule, aad_encode_roles.cuh: enc_fast_launch */
 
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -555,13 +555,14 @@ inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((
 }  // namespace
 
 #include "aad_encode_fast.cuh"
+#include "aad_encode_roles.cuh"
 #include "aad_decode_fast.cuh"
 
 extern "C" {
 
 uint64_t aadk_launch_count(void) { return g_launches; }
 void aadk_force_generic(int on) { g_force_generic = (on == 1); g_dec_wide_all = (on == 2); }
-void aadk_set_encoder_pairing(int on) { g_enc_pairing = on ? 1 : 0; }
+void aadk_set_encoder_schedule(int mode) { g_enc_schedule = (mode >= 0 && mode <= 4) ? mode : 1; }
 
 int aadk_decode_interleaved_ok(const struct aadk_decode_params *p)
 {

@@ -132,8 +132,11 @@ uint64_t aadk_launch_count(void);
 /* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths;
  * 2 = decode mono / stereo streams with the any-channel-count staged kernel (aad_decode_wide) too */
 void aadk_force_generic(int on);
-/* tests / measurement: 0 = the encoder never runs two passes interleaved in one thread (default 1 = when chains are scarce) */
-void aadk_set_encoder_pairing(int on);
+/* tests / measurement: the fast encoder's pass schedule.  1 (default) = chosen by shape; 0 = one pass at a time in
+ * every thread; 2 = the two independent dry passes of a block interleaved in one thread; 3 = helper lanes run the
+ * baseline passes; 4 = helper lanes + a second warp that runs the emitting passes ahead of the decision.  A forced
+ * schedule applies where the launch qualifies for it.  All of them produce the reference's bytes. */
+void aadk_set_encoder_schedule(int mode);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ class GpuApi:
         "AADGpu_SetMaxChannels", "AADGpu_GetMaxChannels", "AADGpu_HostAlloc", "AADGpu_HostFree", "AADGpu_BindHostThread",
         "AADGpu_StreamBytesBound", "AADGpu_StreamBytes", "AADGpu_EncodeBatchDevice", "AADGpu_DecodeBatchDevice",
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_ReconstructBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
-        "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath", "AADGpu_SetEncoderPairing",
+        "AADGpu_Interleave16Device", "AADGpu_SynthLut", "AADGpu_SetKernelPath", "AADGpu_SetEncoderPairing", "AADGpu_SetEncoderSchedule",
         "AADGpu_SetEncodeSegmentBlocks", "AADGpu_GetEncodeSegmentBlocks",
         "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16", "AADGpu_AnalyzeWav", "AADGpu_EncodeWav",
         "AADGpuGroup_Create", "AADGpuGroup_Destroy", "AADGpuGroup_Size", "AADGpuGroup_Device",
@@ -69,6 +69,7 @@ class GpuApi:
             "AADGpu_SynthLut": (None, [vp]),
             "AADGpu_SetKernelPath": (None, [C.c_int]),
             "AADGpu_SetEncoderPairing": (None, [C.c_int]),
+            "AADGpu_SetEncoderSchedule": (None, [C.c_int]),
             "AADGpu_SetEncodeSegmentBlocks": (C.c_int, [C.c_void_p, C.c_uint32]),
             "AADGpu_GetEncodeSegmentBlocks": (C.c_uint32, [C.c_void_p]),
             "AADGpu_EncodeInterleaved16": (C.c_int, [vp, pp, vp, u32, vp, u32, C.POINTER(u32)]),

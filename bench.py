@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--bits", type=int, default=BITS)
     ap.add_argument("--channels", type=int, default=CHANNELS)
     ap.add_argument("--no-pairing", action="store_true", help="encoder: never interleave two passes in one thread")
+    ap.add_argument("--schedule", type=int, default=1, help="encoder pass schedule (AADGpu_SetEncoderSchedule): 1 = by shape")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=96, help="clips in the bounded CPU-baseline sample")
@@ -480,7 +481,7 @@ def run_b200_arm(args):
         idle_group = dist.new_group(backend="gloo")     # host-side waits that keep the waiting ranks' GPUs idle
 
     api, gpu = aad_b200.load()
-    gpu.lib.AADGpu_SetEncoderPairing(0 if args.no_pairing else 1)
+    gpu.lib.AADGpu_SetEncoderSchedule(0 if args.no_pairing else args.schedule)
     ctx = gpu.create(local)
     local_cpus = gpu.lib.AADGpu_BindHostThread(ctx)     # pinned buffers of this rank on the GPU's own NUMA node
     N, ch, n = args.clips, args.channels, args.samples

@@ -57,6 +57,12 @@ void AADGpu_SetKernelPath(int path);
 /* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */
 void AADGpu_SetEncoderPairing(int on);
+/* The fast encoder's pass schedule, for tests and measurement: 1 (default) = chosen by the launch's shape; 0 = one pass
+ * at a time in every thread; 2 = the two independent dry passes of a block interleaved in one thread (few chains);
+ * 3 = helper lanes of every warp run the baseline passes (chains <= 25 per warp scheduler: 5 pass slots per block
+ * instead of 6); 4 = helper lanes plus a second warp running the emitting passes ahead of the decision (a handful of
+ * chains, e.g. ONE long stream: 4 slots).  A forced schedule applies only where the launch qualifies.  Same bytes. */
+void AADGpu_SetEncoderSchedule(int mode);
 
 /* Segment-parallel encoding -- an EXTENSION, NOT byte-identical to the reference encoder.
  * The reference carries the predictor weights and the step index from block to block through the whole stream

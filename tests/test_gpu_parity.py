@@ -248,6 +248,62 @@ def test_encoder_pass_pairing_does_not_change_a_byte(product, gpu_ctx, oracle, b
                 assert rc == 0 and res[0][0][i, :res[0][1][i]].tobytes() == want, (block, trials, i)
 
 
+@pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("channels,ms", [(1, False), (2, True), (2, False), (8, False)])
+def test_encoder_schedules_do_not_change_a_byte(product, gpu_ctx, oracle, bits, channels, ms):
+    """The encoder's pass schedules for scarce chains (aad_encode_roles.cuh): 0 = one pass at a time, 2 = two dry
+    passes interleaved in one thread, 3 = helper lanes run the baseline passes, 4 = helper lanes + a second warp
+    emitting ahead of the decision, 1 = chosen by shape.  Same bytes from all of them, and the oracle's: ragged
+    batches (chains end at different blocks), one and three streams, trials 1..3 (3 falls back to the plain passes)."""
+    _, gpu = product
+    rng = np.random.default_rng(2000 + bits * 10 + channels)
+    for n_streams, n_max in ((37, 4300), (1, 9000), (3, 2500)):
+        lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+        lens[0] = n_max
+        if n_streams > 4:
+            lens[1], lens[2], lens[3] = 3, 4, 5
+        pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+        for i in range(n_streams):
+            pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[(i + bits) % len(aadtest.SIGNALS)], channels, int(lens[i]), 11 * i)
+        for block in (256 * channels // (2 if channels == 8 else 1), 1024):
+            for trials in (1, 2, 3):
+                res = {}
+                for schedule in (0, 1, 2, 3, 4):
+                    gpu.lib.AADGpu_SetEncoderSchedule(schedule)
+                    try:
+                        aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, block, ms, trials, num_samples=lens)
+                    finally:
+                        gpu.lib.AADGpu_SetEncoderSchedule(1)
+                    for i in range(n_streams):
+                        aad[i, sizes[i]:] = 0
+                    res[schedule] = (aad, sizes)
+                for schedule in (1, 2, 3, 4):
+                    assert np.array_equal(res[0][1], res[schedule][1]), (n_streams, block, trials, schedule)
+                    assert np.array_equal(res[0][0], res[schedule][0]), (n_streams, block, trials, schedule)
+                for i in range(0, n_streams, 6):
+                    rc, want = oracle.encode(pcm[i, :, :lens[i]], 44100, bits, block, ms, trials)
+                    assert rc == 0 and res[0][0][i, :res[0][1][i]].tobytes() == want, (n_streams, block, trials, i)
+
+
+def test_encoder_schedules_carry_state_across_launch_slices(product, gpu_ctx, oracle):
+    """AADGpu_EncodeBatch cuts a batch larger than 64 MiB of PCM into block-range slices; the chain state crosses the
+    launches through the device state array in every schedule (first-block rules only in the stream's block 0)."""
+    _, gpu = product
+    n_streams, channels, n = 40, 2, 450_000           # 72 MB of PCM: two slices
+    pcm = np.stack([aadtest.signal("music", channels, n, i) for i in range(n_streams)])
+    res = {}
+    for schedule in (0, 3, 4):
+        gpu.lib.AADGpu_SetEncoderSchedule(schedule)
+        try:
+            res[schedule] = gpu.encode_batch(gpu_ctx, pcm, 44100, 4, 1024, False, 2)
+        finally:
+            gpu.lib.AADGpu_SetEncoderSchedule(1)
+    for schedule in (3, 4):
+        assert np.array_equal(res[0][0], res[schedule][0]) and np.array_equal(res[0][1], res[schedule][1]), schedule
+    rc, want = oracle.encode(pcm[7], 44100, 4, 1024, False, 2)
+    assert rc == 0 and res[0][0][7, :res[0][1][7]].tobytes() == want
+
+
 @pytest.mark.parametrize("bits,channels,ms", [(4, 1, False), (3, 2, True), (2, 8, False)])
 def test_reconstruct_batch_equals_encode_then_decode(product, gpu_ctx, bits, channels, ms):
     """AADGpu_ReconstructBatch = AADGpu_EncodeBatch + AADGpu_DecodeBatch in one sliced pass (ragged lengths,
