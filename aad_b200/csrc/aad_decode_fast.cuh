@@ -30,6 +30,7 @@ namespace {
 constexpr int kDecWarps = AAD_DEC_WARPS;
 constexpr int kDecWindow = 128;           /* samples per chain per window */
 constexpr int kDecOutPitch = 264;         /* 256 + 8: conflict-free 8-byte shared accesses */
+constexpr int kDecBulkPitch = 272;        /* BULK: 16-byte aligned rows (cp.async.bulk), conflict-free 16-byte accesses */
 
 
 /* Dequantised difference per (step row, code) and index delta per magnitude, both in shared memory.
@@ -62,6 +63,7 @@ struct DecGeom {
   static constexpr int SPS = STEP_BYTES * 8 / (BITS * C);  /* samples per chain per step */
   static constexpr int HALF_BYTES = STEP_BYTES / 2;        /* mono only: 18-byte header -> word alignment */
   static constexpr int WARP_BYTES = ((IN_BYTES + 15) & ~15) + 32 * kDecOutPitch;
+  static constexpr int WARP_BYTES_BULK = ((IN_BYTES + 15) & ~15) + 32 * kDecBulkPitch;
 };
 
 template <int BITS>
@@ -162,6 +164,26 @@ __device__ __forceinline__ void dec_emit(unsigned char *orow, uint32_t at, const
   for (int k = 0; k < N; k += 4)
     *reinterpret_cast<uint2 *>(orow + 2 * (at + k)) = make_uint2(dec_pack2(o[k], o[k + 1]), dec_pack2(o[k + 2], o[k + 3]));
 }
+
+/* BULK: 8 samples as one 16-byte store (at % 8 == 0, rows 16-byte aligned) */
+__device__ __forceinline__ void dec_emit8(unsigned char *orow, uint32_t at, const int32_t *o)
+{
+  *reinterpret_cast<uint4 *>(orow + 2 * at) =
+      make_uint4(dec_pack2(o[0], o[1]), dec_pack2(o[2], o[3]), dec_pack2(o[4], o[5]), dec_pack2(o[6], o[7]));
+}
+
+/* BULK flush: `bytes` (a multiple of 16) of this lane's shared output row to its global row through the TMA unit
+ * (cp.async.bulk, shared -> global).  The lane wrote the row itself: a proxy fence orders its stores before the
+ * asynchronous read, no warp synchronisation is involved. */
+__device__ __forceinline__ void dec_bulk_store(void *gdst, const unsigned char *srow, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(srow)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dec_bulk_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void dec_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* the bulk reads of this thread's earlier groups have left shared memory: the row may be written again */
+__device__ __forceinline__ void dec_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 /* 16 bytes at q (16-byte aligned) for the shared input rows; bytes at or past `end` -- the end of the stream's
  * valid data -- read as zero, a null q (a loader lane without a chunk) as well */
@@ -310,9 +332,14 @@ __device__ __noinline__ void dec_flush_ragged_frames(const unsigned char *out_ro
   }
 }
 
-template <int BITS, int C, int IL>   /* IL = 1: stereo output in WAV order (frames), formed in the flush */
+/* IL = 1: stereo output in WAV order (frames), formed in the flush.
+ * BULK = 1 (mono 4-bit, where every window of a block is a whole number of 16-byte pieces at a 16-byte aligned place
+ * of the PCM row): every lane hands its own shared output row to the TMA unit (cp.async.bulk shared -> global) instead
+ * of the warp copying 32 rows through registers. */
+template <int BITS, int C, int IL, int BULK = 0>
 __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_decode_params p)
 {
+  static_assert(!BULK || (BITS == 4 && C == 1 && IL == 0), "bulk-store flush: mono 4-bit planar");
   using G = DecGeom<BITS, C>;
   extern __shared__ __align__(16) unsigned char dec_smem[];
   DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
@@ -320,7 +347,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
-  unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)warp * G::WARP_BYTES;
+  unsigned char *in_rows = dec_smem + ((sizeof(DecTables) + 15) & ~(size_t)15) +
+                           (size_t)warp * (BULK ? G::WARP_BYTES_BULK : G::WARP_BYTES);
   unsigned char *out_rows = in_rows + ((G::IN_BYTES + 15) & ~15);
 
   const uint32_t spb = p.geo.samples_per_block;
@@ -380,7 +408,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     /* reader role: this lane's block row in shared memory */
     const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
     const unsigned char *irow = in_rows + row * G::IN_PITCH;
-    unsigned char *orow = out_rows + lane * kDecOutPitch;
+    unsigned char *orow = out_rows + lane * (BULK ? kDecBulkPitch : kDecOutPitch);
     auto in_u8 = [&](uint32_t pos) -> uint32_t { return irow[a_r + pos]; };
 
     DecChain c;
@@ -409,6 +437,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
 
       uint32_t produced = 0;      /* samples this chain wrote into its output row in this window */
       uint32_t pos = 0;           /* byte position inside the window */
+      bool row_busy = BULK != 0;                  /* BULK: the previous window's row may still be on its way out */
       if (w == 0) {
         /* block header, src/aad_decoder.c:364-380: u16 (index << 4 | shift), 4 x (u16 weight, u16 history) */
         const uint32_t hp = AADF_CHANNEL_HEADER_BYTES * ch;
@@ -425,10 +454,21 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
         c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
         c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
         const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };   /* src/aad_decoder.c:386-391 */
-        dec_emit<4>(orow, 0, first4);
+        if (!BULK) dec_emit<4>(orow, 0, first4);
         produced = 4;
         pos = AADF_CHANNEL_HEADER_BYTES * C;
-        if (C == 1) {
+        if (BULK) {
+          /* the 4 header samples and the half step's 4 as one 16-byte piece */
+          const uint32_t v = in_u8(pos) | (in_u8(pos + 1) << 8);
+          int32_t o[8] = { first4[0], first4[1], first4[2], first4[3], 0, 0, 0, 0 };
+          dec_byte<BITS, 0>(c, v, tab, o + 4);
+          dec_byte<BITS, 1>(c, v, tab, o + 6);
+          dec_bulk_wait_read();          /* as late as possible: the row is written for the first time here */
+          row_busy = false;
+          dec_emit8(orow, 0, o);
+          produced = 8;
+          pos += G::HALF_BYTES;
+        } else if (C == 1) {
           /* half a step: the 18-byte header leaves the row 2 bytes off word alignment */
           if (BITS == 3) {
             int32_t o[16];
@@ -497,10 +537,32 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
               dec_byte<BITS, 0>(c, v, tab, o);
               dec_byte<BITS, 2>(c, v, tab, o + PER_BYTE);
             }
-            dec_emit<G::SPS>(orow, produced, o);
+            if (BULK) {
+              if (row_busy) {
+                dec_bulk_wait_read();
+                row_busy = false;
+              }
+              dec_emit8(orow, produced, o);
+            } else {
+              dec_emit<G::SPS>(orow, produced, o);
+            }
           }
           produced += G::SPS;
         }
+      }
+      if (BULK) {
+        /* every lane hands its own row to the TMA unit: whole 16-byte pieces in bulk, a ragged tail (a stream's last
+         * block, a short buffer) by itself */
+        const uint32_t room = n_row > out_base ? n_row - out_base : 0u;
+        const uint32_t count = min(min(produced, spb - out_base), room);
+        const uint32_t whole = count & ~7u;
+        dec_bulk_fence();
+        if (whole) dec_bulk_store(grow + out_base, orow, whole * 2u);
+        dec_bulk_commit();
+        for (uint32_t k = whole; k < count; k++) grow[out_base + k] = *reinterpret_cast<const int16_t *>(orow + 2u * k);
+        out_base += produced;
+        __syncwarp();                 /* every lane is done with the input rows before the next window is staged */
+        continue;
       }
       __syncwarp();
 
@@ -547,6 +609,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       __syncwarp();
     }
   }
+  if (BULK) dec_bulk_wait_read();   /* shared memory stays valid until the last rows have been read */
 }
 
 /*
@@ -795,20 +858,27 @@ int dec_persistent_grid(K kernel, size_t smem, uint64_t warps, unsigned *grid)
   return 0;
 }
 
-template <int BITS, int C, int IL>
+template <int BITS, int C, int IL, int BULK = 0>
 int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
 {
   using G = DecGeom<BITS, C>;
-  const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * G::WARP_BYTES;
+  const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (BULK ? G::WARP_BYTES_BULK : G::WARP_BYTES);
   /* per device, so not cached in a static: a process may drive several GPUs */
-  cudaError_t e = cudaFuncSetAttribute(aad_decode_fast<BITS, C, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(aad_decode_fast<BITS, C, IL, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
   unsigned grid = 0;
-  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C, IL>, smem, warps, &grid)) return rc;
-  aad_decode_fast<BITS, C, IL><<<grid, kDecWarps * 32, smem, s>>>(p);
+  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C, IL, BULK>, smem, warps, &grid)) return rc;
+  aad_decode_fast<BITS, C, IL, BULK><<<grid, kDecWarps * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
+}
+
+/* the TMA flush needs every window of every block to start at a 16-byte aligned place of its PCM row */
+inline bool dec_bulk_eligible(const aadk_decode_params &p)
+{
+  return g_dec_bulk != 0 && p.geo.bits == 4 && p.geo.channels == 1 && !p.interleaved && p.geo.samples_per_block % 8u == 0 &&
+         ((uintptr_t)p.pcm & 15u) == 0 && p.pcm_clip_stride % 8u == 0 && p.sample_base % 8u == 0;
 }
 
 template <int BITS>
@@ -833,7 +903,10 @@ template <int BITS>
 int dec_fast_launch(const aadk_decode_params &p, cudaStream_t s)
 {
   if (p.geo.channels > 2 || (g_dec_wide_all && !p.interleaved)) return dec_wide_launch<BITS>(p, s);
-  if (p.geo.channels == 1) return dec_fast_launch_bc<BITS, 1, 0>(p, s);   /* mono: WAV order is the plane itself */
+  if (p.geo.channels == 1) {   /* mono: WAV order is the plane itself */
+    if (BITS == 4 && dec_bulk_eligible(p)) return dec_fast_launch_bc<(BITS == 4 ? 4 : BITS), 1, 0, (BITS == 4 ? 1 : 0)>(p, s);
+    return dec_fast_launch_bc<BITS, 1, 0>(p, s);
+  }
   return p.interleaved ? dec_fast_launch_bc<BITS, 2, 1>(p, s) : dec_fast_launch_bc<BITS, 2, 0>(p, s);
 }
 

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 static __thread char tl_error[320] = "";
 static uint32_t g_max_channels = AADF_MAX_CHANNELS;
@@ -106,6 +107,7 @@ struct AADGpu *AADGpu_Create(int device)
   for (int i = 0; i < AADGPU_MAX_SLICES && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_run[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_out[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     aadgpu_fail("AADGpu_Create", e);
@@ -126,6 +128,11 @@ void AADGpu_Destroy(struct AADGpu *g)
   for (int i = 0; i < AADGPU_MAX_SLICES; i++) {
     if (g->ev_in[i]) cudaEventDestroy(g->ev_in[i]);
     if (g->ev_run[i]) cudaEventDestroy(g->ev_run[i]);
+    if (g->ev_out[i]) cudaEventDestroy(g->ev_out[i]);
+  }
+  for (int i = 0; i < 3; i++) {
+    if (g->ring_in[i]) cudaFreeHost(g->ring_in[i]);
+    if (g->ring_out[i]) cudaFreeHost(g->ring_out[i]);
   }
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_run) cudaStreamDestroy(g->s_run);
@@ -788,32 +795,183 @@ AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatc
 }
 
 /* ---- single-stream paths behind the drop-in API ------------------------------------------- */
+/*
+ * AADEncoder_EncodeWhole / AADDecoder_DecodeWhole hand over what src/main.c:94-103,169-172 allocates: plain malloc'd
+ * memory, one int32 per 16-bit sample.  Copying that as it is would move 4 bytes per sample through the driver's own
+ * staging, one synchronous piece at a time.  Instead the stream is cut into slices that travel through a small ring of
+ * pinned buffers as int16 (2 bytes per sample on the link), and the conversion int32 <-> int16 is done by a few host
+ * threads while they move the samples between the caller's rows and the ring -- the only place where every sample has
+ * to be touched by the host anyway.  While slice k is converted, slice k+1 is on the link and slice k+2 in the kernel.
+ */
+#define AADGPU_RING_SLOTS 3
+#define AADGPU_RING_BYTES ((size_t)16 << 20)      /* per slot and direction */
+#define AADGPU_MAX_HOST_THREADS 8
+
+/* a minimal fork-join pool: run fn(arg, i) for i in [0, n) on the calling thread and up to 7 helpers */
+struct host_pool {
+  pthread_mutex_t lock;
+  pthread_cond_t wake, done;
+  pthread_t threads[AADGPU_MAX_HOST_THREADS];
+  int num_threads, started;
+  void (*fn)(void *, uint32_t);
+  void *arg;
+  uint32_t next, total, finished;
+  uint64_t generation;
+};
+static struct host_pool g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+                                   {0}, 0, 0, NULL, NULL, 0, 0, 0, 0 };
+static pthread_mutex_t g_pool_user = PTHREAD_MUTEX_INITIALIZER;   /* one parallel_for at a time */
+
+static void *host_pool_worker(void *unused)
+{
+  (void)unused;
+  uint64_t seen = 0;
+  pthread_mutex_lock(&g_pool.lock);
+  for (;;) {
+    while (g_pool.generation == seen || g_pool.next >= g_pool.total) {
+      seen = g_pool.generation;
+      pthread_cond_wait(&g_pool.wake, &g_pool.lock);
+    }
+    while (g_pool.next < g_pool.total) {
+      const uint32_t i = g_pool.next++;
+      void (*fn)(void *, uint32_t) = g_pool.fn;
+      void *arg = g_pool.arg;
+      pthread_mutex_unlock(&g_pool.lock);
+      fn(arg, i);
+      pthread_mutex_lock(&g_pool.lock);
+      if (++g_pool.finished == g_pool.total) pthread_cond_signal(&g_pool.done);
+    }
+    seen = g_pool.generation;
+  }
+  return NULL;
+}
+
+static void host_parallel_for(uint32_t n, void (*fn)(void *, uint32_t), void *arg)
+{
+  if (n == 0) return;
+  pthread_mutex_lock(&g_pool_user);
+  pthread_mutex_lock(&g_pool.lock);
+  if (!g_pool.started) {
+    long cpus = sysconf(_SC_NPROCESSORS_ONLN);
+    int want = (int)(cpus > 1 ? cpus - 1 : 0);
+    if (want > AADGPU_MAX_HOST_THREADS - 1) want = AADGPU_MAX_HOST_THREADS - 1;
+    for (int t = 0; t < want; t++)
+      if (pthread_create(&g_pool.threads[g_pool.num_threads], NULL, host_pool_worker, NULL) == 0) {
+        pthread_detach(g_pool.threads[g_pool.num_threads]);
+        g_pool.num_threads++;
+      }
+    g_pool.started = 1;
+  }
+  g_pool.fn = fn;
+  g_pool.arg = arg;
+  g_pool.next = 0;
+  g_pool.total = n;
+  g_pool.finished = 0;
+  g_pool.generation++;
+  pthread_cond_broadcast(&g_pool.wake);
+  while (g_pool.next < g_pool.total) {          /* the caller works too (and alone when no helper could be started) */
+    const uint32_t i = g_pool.next++;
+    pthread_mutex_unlock(&g_pool.lock);
+    fn(arg, i);
+    pthread_mutex_lock(&g_pool.lock);
+    g_pool.finished++;
+  }
+  while (g_pool.finished < g_pool.total) pthread_cond_wait(&g_pool.done, &g_pool.lock);
+  g_pool.total = 0;
+  pthread_mutex_unlock(&g_pool.lock);
+  pthread_mutex_unlock(&g_pool_user);
+}
+
+/* one conversion job: `rows` rows, samples [0, n) each, cut into pieces of kConvPiece samples */
+enum { kConvPiece = 1 << 18 };
+struct conv_job {
+  int widen;                       /* 1: ring int16 -> caller int32, 0: caller int32 -> ring int16 */
+  uint32_t rows, pieces_per_row;
+  uint64_t n;                      /* samples per row in this slice */
+  int16_t *ring;                   /* [rows][n] */
+  int32_t *const *wide;            /* caller rows */
+  uint64_t first;                  /* first sample of the slice in the caller's rows */
+};
+
+static void conv_piece(void *arg, uint32_t i)
+{
+  const struct conv_job *j = (const struct conv_job *)arg;
+  const uint32_t r = i / j->pieces_per_row, k = i % j->pieces_per_row;
+  const uint64_t a = (uint64_t)k * kConvPiece, b = (a + kConvPiece < j->n) ? a + kConvPiece : j->n;
+  int16_t *narrow = j->ring + (uint64_t)r * j->n;
+  int32_t *wide = j->wide[r] + j->first;
+  if (j->widen) for (uint64_t t = a; t < b; t++) wide[t] = narrow[t];
+  else for (uint64_t t = a; t < b; t++) narrow[t] = (int16_t)wide[t];   /* int16-range values: src/aad_encoder.c:451,612 */
+}
+
+static void convert_rows(int widen, int16_t *ring, int32_t *const *wide, uint32_t rows, uint64_t first, uint64_t n)
+{
+  struct conv_job j;
+  j.widen = widen;
+  j.rows = rows;
+  j.n = n;
+  j.pieces_per_row = (uint32_t)((n + kConvPiece - 1) / kConvPiece);
+  j.ring = ring;
+  j.wide = wide;
+  j.first = first;
+  host_parallel_for(rows * j.pieces_per_row, conv_piece, &j);
+}
+
+struct copy_job { uint8_t *dst; const uint8_t *src; size_t bytes; };
+enum { kCopyPiece = 1 << 20 };
+static void copy_piece(void *arg, uint32_t i)
+{
+  const struct copy_job *j = (const struct copy_job *)arg;
+  const size_t a = (size_t)i * kCopyPiece, b = (a + kCopyPiece < j->bytes) ? a + kCopyPiece : j->bytes;
+  memcpy(j->dst + a, j->src + a, b - a);
+}
+static void copy_bytes(uint8_t *dst, const uint8_t *src, size_t bytes)
+{
+  struct copy_job j = { dst, src, bytes };
+  host_parallel_for((uint32_t)((bytes + kCopyPiece - 1) / kCopyPiece), copy_piece, &j);
+}
+
+static int ring_ready(struct AADGpu *gpu)
+{
+  for (int i = 0; i < AADGPU_RING_SLOTS; i++) {
+    if (!gpu->ring_in[i] && cudaMallocHost(&gpu->ring_in[i], AADGPU_RING_BYTES) != cudaSuccess) goto fail;
+    if (!gpu->ring_out[i] && cudaMallocHost(&gpu->ring_out[i], AADGPU_RING_BYTES) != cudaSuccess) goto fail;
+  }
+  return 1;
+fail:
+  aadgpu_fail("cudaMallocHost (bounce ring)", cudaGetLastError());
+  return 0;
+}
+
+/* blocks per slice so that a slice's int16 samples (all channels) and its encoded bytes both fit a ring slot */
+static uint32_t ring_slice_blocks(const struct aadf_geometry *geo)
+{
+  const uint64_t per_block = (uint64_t)geo->channels * geo->samples_per_block * 2;
+  uint64_t n = AADGPU_RING_BYTES / (per_block > geo->block_size ? per_block : geo->block_size);
+  return (uint32_t)(n ? n : 1);
+}
 
 static AADApiResult aadgpu_encode_stream_i32_unlocked(struct AADGpu *gpu, const struct aadf_geometry *geo, uint32_t sampling_rate,
                                       uint32_t trials, const int32_t *const *input, uint32_t num_samples,
                                       int32_t *state, uint8_t *data, uint32_t *output_size)
 {
-  const uint32_t C = geo->channels;
+  const uint32_t C = geo->channels, spb = geo->samples_per_block, bs = geo->block_size;
   CU(cudaSetDevice(gpu->device), "cudaSetDevice");
   const uint64_t pitch = round_up64(num_samples, 64);
-  const uint64_t bytes = aadf_stream_bytes(num_samples, C, geo->bits, geo->block_size, geo->samples_per_block);
-  const uint64_t bound = aadf_stream_bytes_bound(num_samples, geo->block_size, geo->samples_per_block);
-  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;    /* int32 rows as given */
+  const uint64_t bytes = aadf_stream_bytes(num_samples, C, geo->bits, bs, spb);
+  const uint64_t bound = aadf_stream_bytes_bound(num_samples, bs, spb);
+  const uint32_t nblk = aadf_num_blocks(num_samples, spb);
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;    /* int16 rows for the kernel */
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)bound + 128)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->state, (size_t)C * AADK_STATE_WORDS * 4)) return AAD_APIRESULT_NG;
-  int32_t *d_in = (int32_t *)gpu->wav.ptr;
-  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
-  cudaStream_t s = gpu->s_run;
-  for (uint32_t c = 0; c < C; c++)
-    CU(cudaMemcpyAsync(d_in + c * pitch, input[c], (size_t)num_samples * 4, cudaMemcpyHostToDevice, s), "H2D pcm");
-  /* the reference API carries 16-bit samples in int32 (src/aad_encoder.c:451,612): narrow on the device
-   * and run the same int16 kernels as every other path */
-  CU((cudaError_t)aadk_launch_narrow32(d_in, pitch, (int16_t *)gpu->pcm.ptr, pitch, C, num_samples, s), "narrow kernel launch");
-  CU(cudaMemcpyAsync(gpu->state.ptr, state, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyHostToDevice, s), "H2D state");
+  if (!ring_ready(gpu)) return AAD_APIRESULT_NG;
+  int16_t *d_pcm = (int16_t *)gpu->pcm.ptr;
+  uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;      /* block 0 lands 32-byte aligned */
+  CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)bound + 128, gpu->s_run), "memset aad");
+  CU(cudaMemcpyAsync(gpu->state.ptr, state, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D state");
   struct aadk_encode_params p;
   memset(&p, 0, sizeof(p));
-  p.pcm = gpu->pcm.ptr;
+  p.pcm = d_pcm;
   p.pcm_clip_stride = (uint64_t)C * pitch;
   p.pcm_ch_stride = pitch;
   p.uniform_samples = num_samples;
@@ -825,12 +983,47 @@ static AADApiResult aadgpu_encode_stream_i32_unlocked(struct AADGpu *gpu, const 
   p.aad_stride = bound;
   p.state_in = (const int32_t *)gpu->state.ptr;
   p.state_out = (int32_t *)gpu->state.ptr;
-  p.block_begin = 0;
-  p.block_end = aadf_num_blocks(num_samples, geo->samples_per_block);
-  CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
-  CU(cudaMemcpyAsync(data, d_aad, (size_t)bytes, cudaMemcpyDeviceToHost, s), "D2H aad");
-  CU(cudaMemcpyAsync(state, gpu->state.ptr, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyDeviceToHost, s), "D2H state");
-  CU(cudaStreamSynchronize(s), "sync");
+
+  /* slice k: narrow the caller's int32 rows into ring slot k % R | H2D | encode its blocks (the chain state crosses
+   * the launches in the device state array, as in the batch pipelines) | D2H its bytes | copy them to the caller */
+  const uint32_t per = ring_slice_blocks(geo);
+  const uint32_t slices = (nblk + per - 1) / per;
+  const uint32_t lag = AADGPU_RING_SLOTS - 1;
+  for (uint32_t k = 0; k < slices + lag; k++) {
+    if (k < slices) {
+      const uint32_t slot = k % AADGPU_RING_SLOTS;
+      const uint32_t b0 = k * per, b1 = (b0 + per < nblk) ? b0 + per : nblk;
+      const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < num_samples) ? (uint64_t)b1 * spb : num_samples;
+      if (k >= AADGPU_RING_SLOTS) CU(cudaEventSynchronize(gpu->ev_in[slot]), "ring wait");   /* slot's last H2D has left it */
+      convert_rows(0, (int16_t *)gpu->ring_in[slot], (int32_t *const *)input, C, s0, s1 - s0);
+      for (uint32_t c = 0; c < C; c++)
+        CU(cudaMemcpyAsync(d_pcm + c * pitch + s0, (int16_t *)gpu->ring_in[slot] + (uint64_t)c * (s1 - s0), (size_t)(s1 - s0) * 2,
+                           cudaMemcpyHostToDevice, gpu->s_in), "H2D pcm");
+      CU(cudaEventRecord(gpu->ev_in[slot], gpu->s_in), "event");
+      CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[slot], 0), "wait");
+      p.block_begin = b0;
+      p.block_end = b1;
+      CU((cudaError_t)aadk_launch_encode(&p, gpu->s_run), "encode kernel launch");
+      CU(cudaEventRecord(gpu->ev_run[slot], gpu->s_run), "event");
+      CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[slot], 0), "wait");
+      const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+      size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+      if (end > bytes) end = (size_t)bytes;
+      CU(cudaMemcpyAsync(gpu->ring_out[slot], d_aad + off, end - off, cudaMemcpyDeviceToHost, gpu->s_out), "D2H aad");
+      CU(cudaEventRecord(gpu->ev_out[slot], gpu->s_out), "event");
+    }
+    if (k >= lag) {
+      const uint32_t j = k - lag, slot = j % AADGPU_RING_SLOTS;
+      const uint32_t b0 = j * per, b1 = (b0 + per < nblk) ? b0 + per : nblk;
+      const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+      size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+      if (end > bytes) end = (size_t)bytes;
+      CU(cudaEventSynchronize(gpu->ev_out[slot]), "ring wait");
+      copy_bytes(data + off, (const uint8_t *)gpu->ring_out[slot], end - off);
+    }
+  }
+  CU(cudaMemcpyAsync(state, gpu->state.ptr, (size_t)C * AADK_STATE_WORDS * 4, cudaMemcpyDeviceToHost, gpu->s_run), "D2H state");
+  CU(cudaStreamSynchronize(gpu->s_run), "sync");
   *output_size = (uint32_t)bytes;
   return AAD_APIRESULT_OK;
 }
@@ -856,10 +1049,9 @@ static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const 
   uint64_t span = AADF_FILE_HEADER_BYTES + (uint64_t)num_blocks * bs;
   if (span > data_size) span = data_size;
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;    /* int16 rows from the kernel */
-  if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * pitch * 4)) return AAD_APIRESULT_NG;    /* int32 rows for the caller */
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + 128)) return AAD_APIRESULT_NG;
+  if (!ring_ready(gpu)) return AAD_APIRESULT_NG;
   int16_t *d_pcm = (int16_t *)gpu->pcm.ptr;
-  int32_t *d_out = (int32_t *)gpu->wav.ptr;
   uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
 
   struct aadk_decode_params p;
@@ -875,29 +1067,44 @@ static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const 
   p.pcm_clip_stride = (uint64_t)C * pitch;
   p.pcm_ch_stride = pitch;
 
-  const uint32_t slices = pick_slices(total * C * 4, num_blocks);
-  for (uint32_t k = 0; k < slices; k++) {
-    const uint32_t b0 = (uint32_t)((uint64_t)num_blocks * k / slices);
-    const uint32_t b1 = (uint32_t)((uint64_t)num_blocks * (k + 1) / slices);
-    const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < total) ? (uint64_t)b1 * spb : total;
-    const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
-    size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
-    if (end > span) end = span;
-    CU(cudaMemcpyAsync(d_aad + off, data + off, end - off, cudaMemcpyHostToDevice, gpu->s_in), "H2D aad");
-    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
-    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
-    p.block_begin = b0;
-    p.block_end = b1;
-    CU((cudaError_t)aadk_launch_decode(&p, gpu->s_run), "decode kernel launch");
-    if (s1 > s0)   /* widen to the API's sample type on the device */
-      CU((cudaError_t)aadk_launch_widen16(d_pcm, pitch, d_out, pitch, C, s0, s1 - s0, gpu->s_run), "widen kernel launch");
-    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
-    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
-    for (uint32_t c = 0; c < C && s1 > s0; c++)
-      CU(cudaMemcpyAsync(buffer[c] + s0, d_out + c * pitch + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost,
-                         gpu->s_out), "D2H pcm");
+  /* slice k: the caller's bytes into ring slot k % R | H2D | decode its blocks | D2H its int16 rows into the ring |
+   * widen them into the caller's int32 rows (host threads) */
+  const uint32_t per = ring_slice_blocks(geo);
+  const uint32_t slices = (num_blocks + per - 1) / per;
+  const uint32_t lag = AADGPU_RING_SLOTS - 1;
+  for (uint32_t k = 0; k < slices + lag; k++) {
+    if (k < slices) {
+      const uint32_t slot = k % AADGPU_RING_SLOTS;
+      const uint32_t b0 = k * per, b1 = (b0 + per < num_blocks) ? b0 + per : num_blocks;
+      const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < total) ? (uint64_t)b1 * spb : total;
+      const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
+      size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
+      if (end > span) end = (size_t)span;
+      if (k >= AADGPU_RING_SLOTS) CU(cudaEventSynchronize(gpu->ev_in[slot]), "ring wait");
+      if (end > off) {
+        copy_bytes((uint8_t *)gpu->ring_in[slot], data + off, end - off);
+        CU(cudaMemcpyAsync(d_aad + off, gpu->ring_in[slot], end - off, cudaMemcpyHostToDevice, gpu->s_in), "H2D aad");
+      }
+      CU(cudaEventRecord(gpu->ev_in[slot], gpu->s_in), "event");
+      CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[slot], 0), "wait");
+      p.block_begin = b0;
+      p.block_end = b1;
+      CU((cudaError_t)aadk_launch_decode(&p, gpu->s_run), "decode kernel launch");
+      CU(cudaEventRecord(gpu->ev_run[slot], gpu->s_run), "event");
+      CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[slot], 0), "wait");
+      for (uint32_t c = 0; c < C && s1 > s0; c++)
+        CU(cudaMemcpyAsync((int16_t *)gpu->ring_out[slot] + (uint64_t)c * (s1 - s0), d_pcm + c * pitch + s0, (size_t)(s1 - s0) * 2,
+                           cudaMemcpyDeviceToHost, gpu->s_out), "D2H pcm");
+      CU(cudaEventRecord(gpu->ev_out[slot], gpu->s_out), "event");
+    }
+    if (k >= lag) {
+      const uint32_t j = k - lag, slot = j % AADGPU_RING_SLOTS;
+      const uint32_t b0 = j * per, b1 = (b0 + per < num_blocks) ? b0 + per : num_blocks;
+      const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < total) ? (uint64_t)b1 * spb : total;
+      CU(cudaEventSynchronize(gpu->ev_out[slot]), "ring wait");
+      if (s1 > s0) convert_rows(1, (int16_t *)gpu->ring_out[slot], buffer, C, s0, s1 - s0);
+    }
   }
-  CU(cudaStreamSynchronize(gpu->s_out), "sync");
   return AAD_APIRESULT_OK;
 }
 

@@ -30,7 +30,8 @@ struct AADGpu {
   int device;
   pthread_mutex_t lock;
   cudaStream_t s_in, s_run, s_out;
-  cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES];
+  cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES], ev_out[AADGPU_MAX_SLICES];
+  void *ring_in[3], *ring_out[3];   /* pinned bounce buffers of the drop-in paths (caller memory is pageable), lazily allocated */
   struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2, raw, stats;
   int lut_ready;
   uint32_t segment_blocks;   /* AADGpu_SetEncodeSegmentBlocks; 0 = the reference's whole-stream state carry */

@@ -130,7 +130,9 @@ int aadk_launch_analysis_stats(const uint8_t *data, uint32_t bits, const int16_t
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t aadk_launch_count(void);
 /* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths;
- * 2 = decode mono / stereo streams with the any-channel-count staged kernel (aad_decode_wide) too */
+ * 2 = decode mono / stereo streams with the any-channel-count staged kernel (aad_decode_wide) too;
+ * 4 = mono 4-bit decode flushes its output rows through the TMA unit (cp.async.bulk shared -> global; the A/B of
+ *     profiles/r02_decoder_experiments.md: bit-exact, 9 % slower than the register flush, hence not the default) */
 void aadk_force_generic(int on);
 /* tests / measurement: the fast encoder's pass schedule.  1 (default) = chosen by shape; 0 = one pass at a time in
  * every thread; 2 = the two independent dry passes of a block interleaved in one thread; 3 = helper lanes run the

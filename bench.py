@@ -358,7 +358,29 @@ def run_long_stream(name, spec, args, torch, api, gpu, ctx, dev, check, world, p
     # ---- decode parity: whole stream against the reference (config 3), sampled blocks one by one (config 4)
     data = aad[0, :size].cpu().numpy()
     dec_h = out[0].cpu().numpy()
-    if samples <= 400_000_000:
+    def decode_whole_call(capi_lib, reps):
+        """AADDecoder_DecodeWhole of `capi_lib` on the stream with plain malloc'd buffers -> (seconds per call, int32 rows)"""
+        from aad_b200.capi import _planar_pointers
+        blob = np.frombuffer(data.tobytes(), dtype=np.uint8)           # a pageable copy
+        rows = [np.zeros(n, dtype=np.int32) for _ in range(ch)]        # touched: page faults are not part of the call
+        ptrs = _planar_pointers(rows)
+        handle = capi_lib.AADDecoder_Create(None, 0)
+        secs = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            rc = capi_lib.AADDecoder_DecodeWhole(handle, blob.ctypes.data_as(C.POINTER(C.c_uint8)), len(blob), ptrs, ch, n)
+            secs.append(time.perf_counter() - t0)
+            check(rc, "AADDecoder_DecodeWhole")
+        capi_lib.AADDecoder_Destroy(handle)
+        return min(secs[1:]) if len(secs) > 1 else secs[0], rows
+
+    ref_decode_s = None
+    if samples <= 400_000_000 and codec.kind == "reference":
+        ref_decode_s, want_rows = decode_whole_call(codec.api.lib, 1)
+        parity["decode"] = {"checked": "whole stream", "samples": samples,
+                            "bit_exact": bool(all(np.array_equal(want_rows[c], dec_h[c]) for c in range(ch)))}
+        del want_rows
+    elif samples <= 400_000_000:
         want_pcm = codec.decode(data.tobytes())
         parity["decode"] = {"checked": "whole stream", "samples": samples, "bit_exact": bool(np.array_equal(want_pcm, dec_h))}
         del want_pcm
@@ -434,6 +456,19 @@ def run_long_stream(name, spec, args, torch, api, gpu, ctx, dev, check, world, p
         res["decode_e2e_group"] = e2e_entry(dt_g, world, size, samples * 2, np.array_equal(h_wav, want_wav),
                                             "AADGpuGroup_DecodeInterleaved16: blocks shared out over all local GPUs, one host thread each")
         res["decode_e2e_group"]["speedup_vs_1_device"] = round(dt / dt_g, 3)
+
+    # ---- the drop-in call itself: AADDecoder_DecodeWhole with plain malloc'd buffers, int32 samples (what
+    #      src/main.c:94-108 does), next to the reference's own time for the same call on one host core
+    if ref_decode_s is not None:
+        dt_d, rows = decode_whole_call(api.lib, 3)
+        same = all(np.array_equal(rows[c], want_wav[:, c]) for c in range(ch))
+        res["dropin_e2e"] = {
+            "call": "AADDecoder_DecodeWhole(malloc'd .aad, malloc'd int32 rows), as src/main.c:94-108 calls it",
+            "ms": round(dt_d * 1e3, 3), "msamples_s": round(samples / dt_d / 1e6, 1), "equals_device_resident_result": bool(same),
+            "vs_pinned_int16_path": round(res["decode_e2e"]["ms"] / (dt_d * 1e3), 3),
+            "reference_same_call_ms": round(ref_decode_s * 1e3, 1), "speedup_vs_reference_one_core": round(ref_decode_s / dt_d, 1),
+            "how": "slices through a ring of pinned buffers as int16; host threads widen to int32 while they copy"}
+        del rows
 
     # ---- segment-mode encode end to end (extension): WAV-order PCM in pinned memory -> .aad in pinned memory
     h_wav[...] = pcm[0].t().contiguous().cpu().numpy()

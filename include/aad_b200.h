@@ -51,8 +51,9 @@ void AADGpu_SetMaxChannels(uint32_t max_channels);       /* 2 = stock reference 
 uint32_t AADGpu_GetMaxChannels(void);
 /* 0 (default): fast kernels wherever the shape allows (mono / stereo: aad_decode_fast, 3..8 channels:
  * aad_decode_wide), generic kernels otherwise; 1: always the generic (any channel count / alignment)
- * kernels; 2: like 0, but mono / stereo streams are decoded by aad_decode_wide too.  All bit-exact;
- * this exists for testing. */
+ * kernels; 2: like 0, but mono / stereo streams are decoded by aad_decode_wide too; 4: like 0, but mono 4-bit
+ * streams leave shared memory through the TMA unit (cp.async.bulk).  All bit-exact; this exists for testing and
+ * measurement. */
 void AADGpu_SetKernelPath(int path);
 /* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */

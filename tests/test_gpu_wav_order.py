@@ -46,6 +46,35 @@ def test_wav_order_decode_matches_oracle(product, gpu_ctx, oracle, bits, channel
             assert np.array_equal(out.T, want), (bits, channels, ms, block, n, cut)
 
 
+def test_tma_bulk_store_flush_is_bit_exact(product, gpu_ctx, oracle):
+    """kernel path 4: mono 4-bit rows leave shared memory through cp.async.bulk (measured slower, off by default):
+    ragged batch, truncated streams, against the default path and the oracle"""
+    _, gpu = product
+    rng = np.random.default_rng(77)
+    n_streams, n_max = 70, 30000
+    lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+    lens[0], lens[1], lens[2] = n_max, 4, 2016 * 3
+    pcm = np.zeros((n_streams, 1, n_max), dtype=np.int16)
+    for i in range(n_streams):
+        pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], 1, int(lens[i]), i)
+    aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, 4, 1024, False, 0, num_samples=lens)
+    cut = sizes.copy()
+    for i in range(3, n_streams, 5):
+        cut[i] = max(31, int(sizes[i]) - int(rng.integers(0, 2048)))
+    res = []
+    for path in (0, 4):
+        gpu.lib.AADGpu_SetKernelPath(path)
+        try:
+            res.append((gpu.decode_batch(gpu_ctx, aad, n_max, 44100, 1, 4, 1024, False, sizes=sizes),
+                        gpu.decode_batch(gpu_ctx, aad, n_max, 44100, 1, 4, 1024, False, sizes=cut)))
+        finally:
+            gpu.lib.AADGpu_SetKernelPath(0)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for i in range(0, n_streams, 9):
+        _, want, _ = oracle.decode(aad[i, :sizes[i]].tobytes())
+        assert np.array_equal(res[1][0][i, :, :lens[i]], want), i
+
+
 @pytest.mark.parametrize("path", [0, 1, 2])
 def test_wav_order_decode_on_every_kernel_path(product, gpu_ctx, oracle, path):
     """kernel path 1 (generic kernels) has no WAV-order flush: planes + one interleave pass, same samples"""
