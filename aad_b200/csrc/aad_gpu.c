@@ -485,6 +485,8 @@ static uint64_t round_up64(uint64_t v, uint64_t m) { return (v + m - 1) / m * m;
 static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
 {
   uint64_t s = pcm_bytes / ((uint64_t)32 << 20);
+  const char *env = getenv("AAD_B200_SLICES");        /* measurement: force the slice count of the batch pipelines */
+  if (env && atoi(env) > 0) s = (uint64_t)atoi(env);
   if (s < 1) s = 1;
   if (s > AADGPU_MAX_SLICES) s = AADGPU_MAX_SLICES;
   if (s > num_blocks) s = num_blocks ? num_blocks : 1;

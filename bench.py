@@ -456,6 +456,9 @@ def run_long_stream(name, spec, args, torch, api, gpu, ctx, dev, check, world, p
         res["decode_e2e_group"] = e2e_entry(dt_g, world, size, samples * 2, np.array_equal(h_wav, want_wav),
                                             "AADGpuGroup_DecodeInterleaved16: blocks shared out over all local GPUs, one host thread each")
         res["decode_e2e_group"]["speedup_vs_1_device"] = round(dt / dt_g, 3)
+        from aad_b200.shard import decode_block_shard      # the same split AADGpuGroup_* makes (aad_gpu.c: split_range)
+        res["decode_e2e_group"]["block_shards"] = [
+            [sh.block_begin, sh.block_end] for sh in (decode_block_shard(n, spb, bs, size, world, r) for r in range(world))]
 
     # ---- the drop-in call itself: AADDecoder_DecodeWhole with plain malloc'd buffers, int32 samples (what
     #      src/main.c:94-108 does), next to the reference's own time for the same call on one host core
@@ -539,7 +542,11 @@ def run_b200_arm(args):
         if rc != 0:
             raise RuntimeError(f"{what}: AADApiResult={rc} {gpu.last_error()}")
 
-    check(gpu.lib.AADGpu_SynthBatchDevice(ctx, bref, rank * N, pcm.data_ptr(), stream), "synth")
+    # this rank's clips of the whole job (weak scaling: N clips per rank, contiguous ranges, no exchange)
+    from aad_b200.shard import decode_block_shard, encode_stream_shard
+    first_clip, last_clip = encode_stream_shard(N * world, world, rank)
+    assert last_clip - first_clip == N
+    check(gpu.lib.AADGpu_SynthBatchDevice(ctx, bref, first_clip, pcm.data_ptr(), stream), "synth")
 
     def step(events=None):
         if events:
