@@ -849,10 +849,9 @@ int dec_persistent_grid(K kernel, size_t smem, uint64_t warps, unsigned *grid)
 {
   const uint64_t ctas = (warps + kDecWarps - 1) / kDecWarps;
   int dev = 0, sms = 148, per_sm = 1;
-  cudaError_t e;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDecWarps * 32, smem)) != cudaSuccess) return (int)e;
+  if (int rc = device_sm_count(&dev, &sms)) return rc;
+  if (int rc = allow_dynamic_smem(kernel, dev, smem)) return rc;
+  if (int rc = resident_ctas(kernel, dev, kDecWarps * 32, smem, &per_sm)) return rc;
   const uint64_t wave = (uint64_t)sms * (uint64_t)(per_sm > 0 ? per_sm : 1);
   *grid = (unsigned)((AAD_DEC_PERSIST && ctas > wave) ? wave : ctas);
   return 0;
@@ -863,9 +862,6 @@ int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
 {
   using G = DecGeom<BITS, C>;
   const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (BULK ? G::WARP_BYTES_BULK : G::WARP_BYTES);
-  /* per device, so not cached in a static: a process may drive several GPUs */
-  cudaError_t e = cudaFuncSetAttribute(aad_decode_fast<BITS, C, IL, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
   unsigned grid = 0;
@@ -888,8 +884,6 @@ int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
   const size_t in_bytes = ((size_t)rows * 16u * ((BITS * C + 1u) | 1u) + 16u + 15u) & ~(size_t)15;
   const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (in_bytes + 32u * kDecOutPitch);
   auto kernel = p.interleaved ? aad_decode_wide<BITS, 1> : aad_decode_wide<BITS, 0>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + rows - 1) / rows);
   unsigned grid = 0;

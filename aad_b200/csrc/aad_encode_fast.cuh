@@ -574,6 +574,8 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
   const uint32_t seg_end = p.segment_blocks ? seg_first + p.segment_blocks : 0xFFFFFFFFu;
   /* the launch's block range counts from the stream's first block, or (segment_relative) from every segment's */
   const uint32_t rel = (p.segment_blocks && p.segment_relative) ? seg_first : 0u;
+  if (p.segment_blocks && p.segment_relative && p.segment_end != 0u && (seg < p.segment_begin || seg >= p.segment_end))
+    return;   /* another device's segment */
   const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), (uint32_t)min((uint64_t)rel + p.block_end, (uint64_t)0xFFFFFFFFu)), seg_end);
   const uint32_t b_begin = max(rel + p.block_begin, seg_first);
   if (p.segment_blocks && b_begin == seg_first) S.w0 = S.w1 = S.w2 = S.w3 = S.idx8 = 0;   /* a segment starts like a new stream */
@@ -655,23 +657,17 @@ int enc_fast_launch_as(const aadk_encode_params &p, cudaStream_t s)
 {
   const uint64_t lanes = (uint64_t)p.num_streams * p.geo.channels * (p.segment_blocks ? p.num_segments : 1u);
   const size_t ring_bytes = (size_t)(PAIR ? 2 : 1) * EncRing<MS>::kWarpBytes;
-  /* per device, so set on every launch (cheap) */
-  cudaError_t e = cudaFuncSetAttribute(aad_encode_fast<BITS, MS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kEncLutBytes + 8 * ring_bytes));
-  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  if (int rc = device_sm_count(&dev, &sms)) return rc;
+  if (int rc = allow_dynamic_smem(aad_encode_fast<BITS, MS, PAIR>, dev, kEncLutBytes + 8 * ring_bytes)) return rc;
   /* The step table is per CTA.  Smallest CTA that keeps every chain resident in one wave, so few
    * chains spread as single warps over all SMs and sub-partitions; otherwise the shape with the
    * most resident threads. */
-  int dev = 0, sms = 148;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
   unsigned block = 0, best_block = 32;
   uint64_t best_resident = 0;
   for (unsigned cand = 32; cand <= 256 && block == 0; cand *= 2) {
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aad_encode_fast<BITS, MS, PAIR>, (int)cand,
-                                                      kEncLutBytes + (cand / 32) * ring_bytes);
-    if (e != cudaSuccess) return (int)e;
+    if (int rc = resident_ctas(aad_encode_fast<BITS, MS, PAIR>, dev, (int)cand, kEncLutBytes + (cand / 32) * ring_bytes, &per_sm)) return rc;
     const uint64_t resident = (uint64_t)per_sm * sms * cand;
     if (resident >= lanes) block = cand;
     if (resident > best_resident) { best_resident = resident; best_block = cand; }

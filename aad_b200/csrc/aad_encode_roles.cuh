@@ -315,8 +315,9 @@ int roles_launch(const aadk_encode_params &p, uint32_t ka, cudaStream_t s)
   const uint64_t chains = (uint64_t)p.num_streams * p.geo.channels;
   const uint64_t warps = (chains + ka - 1) / ka;
   const size_t smem = kEncLutBytes + (size_t)kRolesWarps * EncRing<MS>::kWarpBytes;
-  cudaError_t e = cudaFuncSetAttribute(aad_encode_roles<BITS, MS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 0;
+  if (int rc = device_sm_count(&dev, &sms)) return rc;
+  if (int rc = allow_dynamic_smem(aad_encode_roles<BITS, MS, 0>, dev, smem)) return rc;
   aad_encode_roles<BITS, MS, 0><<<(unsigned)((warps + kRolesWarps - 1) / kRolesWarps), kRolesWarps * 32, smem, s>>>(p, ka);
   return (int)cudaGetLastError();
 }
@@ -342,8 +343,9 @@ int roles_spec_launch(const aadk_encode_params &p, uint32_t ka, cudaStream_t s)
   const uint64_t ctas = (chains + ka - 1) / ka;
   const size_t scratch = (size_t)(ka / C) * (1u + kRolesMaxTrials) * ((p.geo.block_size + 15u) & ~15u);
   const size_t smem = kEncLutBytes + 2u * EncRing<MS>::kWarpBytes + ((sizeof(RolesMail) + 15u) & ~15u) + scratch;
-  cudaError_t e = cudaFuncSetAttribute(aad_encode_roles<BITS, MS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 0;
+  if (int rc = device_sm_count(&dev, &sms)) return rc;
+  if (int rc = allow_dynamic_smem(aad_encode_roles<BITS, MS, 1>, dev, smem)) return rc;
   aad_encode_roles<BITS, MS, 1><<<(unsigned)ctas, 64, smem, s>>>(p, ka);
   return (int)cudaGetLastError();
 }
@@ -358,9 +360,7 @@ int enc_fast_launch(const aadk_encode_params &p, cudaStream_t s)
   const bool ms = p.geo.ms && p.geo.channels >= 2;
   const int mode = g_enc_schedule;
   int dev = 0, sms = 148;
-  cudaError_t e;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+  if (int rc = device_sm_count(&dev, &sms)) return rc;
   if (mode != 0 && mode != 2 && roles_eligible(p)) {
     const uint32_t ka_spec = roles_spec_chain_lanes(p, sms);
     if (ka_spec != 0 && mode != 3)

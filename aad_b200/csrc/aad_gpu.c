@@ -181,6 +181,10 @@ int AADGpu_BindHostThread(struct AADGpu *gpu)
 {
   char bus[32], path[128], list[1024];
   if (!gpu) return 0;
+  if (gpu->cpus_known)   /* the device's CPU list was read before: no file I/O on the per-call worker threads */
+    return gpu->cpus_count > 0 && sched_setaffinity(0, sizeof(gpu->cpus), &gpu->cpus) == 0 ? gpu->cpus_count : 0;
+  gpu->cpus_known = 1;
+  gpu->cpus_count = 0;
   if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), gpu->device) != cudaSuccess) {
     (void)cudaGetLastError();
     return 0;
@@ -204,6 +208,8 @@ int AADGpu_BindHostThread(struct AADGpu *gpu)
     c = end;
   }
   if (count == 0) return 0;
+  gpu->cpus = set;
+  gpu->cpus_count = count;
   return sched_setaffinity(0, sizeof(set), &set) == 0 ? count : 0;
 }
 
@@ -276,6 +282,52 @@ static AADApiResult AADGpu_LinkProbe_unlocked(struct AADGpu *gpu, size_t bytes, 
 AADApiResult AADGpu_LinkProbe(struct AADGpu *gpu, size_t bytes, int repeats, double gbs[3])
 {
   WITH_CONTEXT_LOCK(gpu, AADGpu_LinkProbe_unlocked(gpu, bytes, repeats, gbs));
+}
+
+/* The same measurement for the copies the batch pipelines issue: `rows` rows of `width` bytes, `host_pitch` bytes
+ * apart in a pinned host buffer (a block-range slice of every stream of a batch), packed on the device.  Tells a
+ * slow link from a slow access pattern. */
+static AADApiResult AADGpu_LinkProbeRows_unlocked(struct AADGpu *gpu, size_t rows, size_t width, size_t host_pitch, int repeats,
+                                                  double gbs[3])
+{
+  if (rows == 0 || width == 0 || host_pitch < width || repeats <= 0 || gbs == NULL) return AAD_APIRESULT_INVALID_ARGUMENT;
+  CU(cudaSetDevice(gpu->device), "cudaSetDevice");
+  const size_t dev_bytes = rows * width, host_bytes = rows * host_pitch;
+  if (!aadgpu_reserve(gpu, &gpu->pcm, dev_bytes)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->pcm2, dev_bytes)) return AAD_APIRESULT_NG;
+  void *up = NULL, *down = NULL;
+  if (cudaMallocHost(&up, host_bytes) != cudaSuccess || cudaMallocHost(&down, host_bytes) != cudaSuccess) {
+    if (up) cudaFreeHost(up);
+    return aadgpu_fail("cudaMallocHost (link probe)", cudaGetLastError());
+  }
+  memset(up, 0x5A, host_bytes);
+  memset(down, 0, host_bytes);
+  cudaError_t e = cudaSuccess;
+  for (int mode = 0; mode < 3 && e == cudaSuccess; mode++) {
+    double t0 = 0.0;
+    for (int r = -1; r < repeats && e == cudaSuccess; r++) {
+      if (mode != 1) e = cudaMemcpy2DAsync(gpu->pcm.ptr, width, up, host_pitch, width, rows, cudaMemcpyHostToDevice, gpu->s_in);
+      if (e == cudaSuccess && mode != 0)
+        e = cudaMemcpy2DAsync(down, host_pitch, gpu->pcm2.ptr, width, width, rows, cudaMemcpyDeviceToHost, gpu->s_out);
+      if (r == -1) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_in);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_out);
+        t0 = wall_seconds();
+      }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_in);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(gpu->s_out);
+    gbs[mode] = (double)dev_bytes * repeats * (mode == 2 ? 2.0 : 1.0) / (wall_seconds() - t0) / 1e9;
+  }
+  cudaFreeHost(up);
+  cudaFreeHost(down);
+  if (e != cudaSuccess) return aadgpu_fail_drained(gpu, "link probe (rows)", e);
+  return AAD_APIRESULT_OK;
+}
+
+AADApiResult AADGpu_LinkProbeRows(struct AADGpu *gpu, size_t rows, size_t width, size_t host_pitch, int repeats, double gbs[3])
+{
+  WITH_CONTEXT_LOCK(gpu, AADGpu_LinkProbeRows_unlocked(gpu, rows, width, host_pitch, repeats, gbs));
 }
 
 /* ---- parameter checks ------------------------------------------------------------------- */
@@ -493,11 +545,12 @@ static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
   return (uint32_t)s;
 }
 
-/* one stream (or a shard of one): pieces of ~8 MiB so that even an eighth of an hour-long file overlaps its
- * copies with its kernels; at most AADGPU_MAX_SLICES (one event each), at most `units` */
+/* one stream (or a shard of one): pieces of ~16 MiB so that even an eighth of an hour-long file overlaps its
+ * copies with its kernels, without turning a small shard into dozens of API calls (the calls of the threads of
+ * one process queue up behind each other); at most AADGPU_MAX_SLICES (one event each), at most `units` */
 static uint32_t pick_stream_slices(uint64_t bytes, uint64_t units)
 {
-  uint64_t s = bytes / ((uint64_t)8 << 20);
+  uint64_t s = bytes / ((uint64_t)16 << 20);
   if (s < 1) s = 1;
   if (s > AADGPU_MAX_SLICES) s = AADGPU_MAX_SLICES;
   if (s > units) s = units ? units : 1;
@@ -700,7 +753,7 @@ AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
  * may be NULL when only the reconstruction is wanted. */
 static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm,
                                      const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes,
-                                     int16_t *reconstructed)
+                                     int16_t *reconstructed, int copies_only)
 {
   if (!gpu || !batch || !pcm || !reconstructed) return AAD_APIRESULT_INVALID_ARGUMENT;
   struct aadf_geometry geo;
@@ -728,10 +781,12 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
   int16_t *d_pcm = (int16_t *)gpu->pcm.ptr, *d_out = (int16_t *)gpu->pcm2.ptr;
   uint8_t *d_aad = (uint8_t *)gpu->aad.ptr + 1;
 
-  CU(cudaMemsetAsync(gpu->state.ptr, 0, state_bytes, gpu->s_run), "memset state");
-  CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)N * astride + 128, gpu->s_run), "memset aad");
-  if (num_samples)
-    CU(cudaMemcpyAsync(gpu->lens.ptr, num_samples, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D lengths");
+  if (!copies_only) {
+    CU(cudaMemsetAsync(gpu->state.ptr, 0, state_bytes, gpu->s_run), "memset state");
+    CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)N * astride + 128, gpu->s_run), "memset aad");
+    if (num_samples)
+      CU(cudaMemcpyAsync(gpu->lens.ptr, num_samples, (size_t)N * 4, cudaMemcpyHostToDevice, gpu->s_run), "H2D lengths");
+  }
 
   struct aadk_encode_params e;
   memset(&e, 0, sizeof(e));
@@ -769,14 +824,16 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
     const uint32_t b0 = (uint32_t)((uint64_t)nblk * k / slices), b1 = (uint32_t)((uint64_t)nblk * (k + 1) / slices);
     const uint32_t s0 = b0 * spb, s1 = (b1 * (uint64_t)spb < ns) ? b1 * spb : ns;
     CU(copy_pcm_slice(batch, C, 1, d_pcm, pitch, (int16_t *)pcm, s0, s1, gpu->s_in), "H2D pcm");
-    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
-    CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
-    e.block_begin = d.block_begin = b0;
-    e.block_end = d.block_end = b1;
-    CU((cudaError_t)aadk_launch_encode(&e, gpu->s_run), "encode kernel launch");
-    CU((cudaError_t)aadk_launch_decode(&d, gpu->s_run), "decode kernel launch");
-    CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
-    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    if (!copies_only) {   /* copies_only: the same copies with nothing between them (AADGpu_CopyProbeBatch) */
+      CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
+      CU(cudaStreamWaitEvent(gpu->s_run, gpu->ev_in[k], 0), "wait");
+      e.block_begin = d.block_begin = b0;
+      e.block_end = d.block_end = b1;
+      CU((cudaError_t)aadk_launch_encode(&e, gpu->s_run), "encode kernel launch");
+      CU((cudaError_t)aadk_launch_decode(&d, gpu->s_run), "decode kernel launch");
+      CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
+      CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+    }
     if (aad) {
       const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
       const size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
@@ -785,6 +842,7 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
     }
     CU(copy_pcm_slice(batch, C, 0, d_out, pitch, reconstructed, s0, s1, gpu->s_out), "D2H pcm");
   }
+  if (copies_only) CU(cudaStreamSynchronize(gpu->s_in), "sync");
   CU(cudaStreamSynchronize(gpu->s_out), "sync");
   if (out_sizes)
     for (uint32_t i = 0; i < N; i++)
@@ -796,7 +854,17 @@ AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatc
                                      const uint32_t *num_samples, uint8_t *aad, uint32_t *out_sizes,
                                      int16_t *reconstructed)
 {
-  WITH_CONTEXT_LOCK(gpu, AADGpu_ReconstructBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes, reconstructed));
+  WITH_CONTEXT_LOCK(gpu, AADGpu_ReconstructBatch_unlocked(gpu, batch, pcm, num_samples, aad, out_sizes, reconstructed, 0));
+}
+
+/* Exactly the host <-> device copies AADGpu_ReconstructBatch issues for this batch and these (pinned) buffers -- same
+ * slices, same row shapes, same two streams -- with no kernel and no dependency between them: how long the copies
+ * alone take, i.e. what the end-to-end call could at best reach.  Right after a AADGpu_ReconstructBatch of the same
+ * batch the device buffers still hold its results, so the host buffers receive the same bytes again. */
+AADApiResult AADGpu_CopyProbeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm, uint8_t *aad,
+                                   int16_t *reconstructed)
+{
+  WITH_CONTEXT_LOCK(gpu, AADGpu_ReconstructBatch_unlocked(gpu, batch, pcm, NULL, aad, NULL, reconstructed, 1));
 }
 
 /* ---- single-stream paths behind the drop-in API ------------------------------------------- */
@@ -1210,6 +1278,10 @@ static AADApiResult encode_wav_device(struct AADGpu *gpu, const struct AADEncode
   return AAD_APIRESULT_OK;
 }
 
+static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
+                                        const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
+                                        uint8_t *data);
+
 static AADApiResult AADGpu_EncodeInterleaved16_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm,
                                         const int16_t *interleaved, uint32_t num_samples, uint8_t *data,
                                         uint32_t data_size, uint32_t *output_size)
@@ -1223,6 +1295,14 @@ static AADApiResult AADGpu_EncodeInterleaved16_unlocked(struct AADGpu *gpu, cons
   uint64_t pitch = 0, bytes = 0;
   if (aadf_stream_bytes(num_samples, geo.channels, geo.bits, geo.block_size, geo.samples_per_block) > data_size)
     return AAD_APIRESULT_INSUFFICIENT_BUFFER;
+  if (gpu->segment_blocks != 0) {
+    /* segment mode: the pipeline that is cut across the segments (also what a device group runs per shard) */
+    const AADApiResult es = encode_stream_range_unlocked(gpu, prm, gpu->segment_blocks, interleaved, num_samples, 0,
+                                                         aadf_num_blocks(num_samples, geo.samples_per_block), data);
+    if (es == AAD_APIRESULT_OK)
+      *output_size = (uint32_t)aadf_stream_bytes(num_samples, geo.channels, geo.bits, geo.block_size, geo.samples_per_block);
+    return es;
+  }
   const AADApiResult e = encode_interleaved_device(gpu, prm, &geo, interleaved, num_samples, &pitch, &bytes);
   if (e != AAD_APIRESULT_OK) return e;
   CU(cudaMemcpyAsync(data, (uint8_t *)gpu->aad.ptr + 1, (size_t)bytes, cudaMemcpyDeviceToHost, gpu->s_run), "D2H aad");
@@ -1595,10 +1675,23 @@ static AADApiResult encode_stream_range(struct AADGpu *gpu, const struct AADEnco
                                         const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
                                         uint8_t *data);
 
+/* AAD_B200_TRACE=1: per-shard wall times of the group calls on stderr (diagnosis of multi-device runs) */
+static int trace_on(void)
+{
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("AAD_B200_TRACE");
+    on = (e && atoi(e) > 0) ? 1 : 0;
+  }
+  return on;
+}
+
 static void *group_worker(void *arg)
 {
   struct group_task *t = (struct group_task *)arg;
+  const double t_start = trace_on() ? wall_seconds() : 0.0;
   if (t->bind) (void)AADGpu_BindHostThread(t->gpu);   /* a thread of its own: stay next to its device */
+  const double t_bound = trace_on() ? wall_seconds() : 0.0;
   switch (t->op) {
     case GROUP_ENCODE_BATCH:
       t->result = AADGpu_EncodeBatch(t->gpu, &t->batch, t->pcm_in, t->lens, t->aad_out, t->sizes_out);
@@ -1615,6 +1708,9 @@ static void *group_worker(void *arg)
       break;
   }
   snprintf(t->error, sizeof(t->error), "%s", AADGpu_LastError());   /* thread-local: carry it to the caller */
+  if (trace_on())
+    fprintf(stderr, "[aad_b200] group shard on device %d: op %d blocks [%u, %u): bind %.3f ms, work %.3f ms\n", t->gpu->device,
+            (int)t->op, t->block_begin, t->block_end, 1e3 * (t_bound - t_start), 1e3 * (wall_seconds() - t_bound));
   return NULL;
 }
 
@@ -1622,6 +1718,7 @@ static AADApiResult group_run(struct group_task *tasks, int n)
 {
   pthread_t th[AADGPU_MAX_GROUP];
   int started[AADGPU_MAX_GROUP];
+  const double t_start = trace_on() ? wall_seconds() : 0.0;
   for (int i = 0; i < n; i++) {
     tasks[i].bind = 1;
     started[i] = pthread_create(&th[i], NULL, group_worker, &tasks[i]) == 0;
@@ -1638,6 +1735,7 @@ static AADApiResult group_run(struct group_task *tasks, int n)
       aadgpu_set_error(tasks[i].error);
     }
   }
+  if (trace_on()) fprintf(stderr, "[aad_b200] group call over %d shard(s): %.3f ms\n", n, 1e3 * (wall_seconds() - t_start));
   return r;
 }
 
@@ -1703,6 +1801,7 @@ static AADApiResult decode_stream_range_unlocked(struct AADGpu *gpu, const struc
   const uint32_t C = geo.channels, spb = geo.samples_per_block, bs = geo.block_size, ns = h->num_samples;
   const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < ns) ? (uint64_t)b1 * spb : ns;
   if (b1 <= b0 || s1 <= s0) return AAD_APIRESULT_OK;
+  const double t_enter = trace_on() ? wall_seconds() : 0.0;
   CU(cudaSetDevice(gpu->device), "cudaSetDevice");
   const uint64_t count = s1 - s0;
   const uint64_t byte0 = AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs;
@@ -1732,7 +1831,11 @@ static AADApiResult decode_stream_range_unlocked(struct AADGpu *gpu, const struc
       CU(cudaMemcpyAsync(interleaved + f0 * C, d_wav + (f0 - s0) * C, (size_t)(f1 - f0) * C * 2, cudaMemcpyDeviceToHost, gpu->s_out),
          "D2H wav slice");
   }
+  const double t_queued = trace_on() ? wall_seconds() : 0.0;
   CU(cudaStreamSynchronize(gpu->s_out), "sync");
+  if (trace_on())
+    fprintf(stderr, "[aad_b200] decode range on device %d: %u slice(s), %.1f MB down: queued after %.3f ms, done after %.3f ms\n",
+            gpu->device, slices, (double)count * C * 2 / 1e6, 1e3 * (t_queued - t_enter), 1e3 * (wall_seconds() - t_enter));
   return AAD_APIRESULT_OK;
 }
 
@@ -1779,9 +1882,30 @@ AADApiResult AADGpuGroup_DecodeInterleaved16(struct AADGpuGroup *g, const uint8_
 
 /* ---- one stream ENCODED by a group: segment mode only ------------------------------------------- */
 
-/* blocks [b0, b1) of one stream (b0 on a segment boundary) from interleaved samples [b0*spb, min(b1*spb, ns)):
- * the shard copies only its own samples, encodes its segments as independent chains and writes its own byte
- * range of the caller's stream (the 31-byte file header with block 0) */
+/* rows x width bytes between a host and a device buffer that share one layout (same pitch); rows that would run past
+ * `limit` bytes of the layout are cut there */
+static cudaError_t copy_slice_rows(uint8_t *dst, const uint8_t *src, uint64_t first, uint64_t pitch, uint64_t width, uint32_t rows,
+                                   uint64_t limit, enum cudaMemcpyKind kind, cudaStream_t st)
+{
+  uint32_t whole = 0;          /* leading rows that lie completely below the limit */
+  while (whole < rows && first + (uint64_t)whole * pitch + width <= limit) whole++;
+  if (whole) {
+    const cudaError_t e = copy_rows(dst + first, pitch, src + first, pitch, width, whole, kind, st);
+    if (e != cudaSuccess) return e;
+  }
+  if (whole < rows) {
+    const uint64_t at = first + (uint64_t)whole * pitch;
+    if (at < limit) return cudaMemcpyAsync(dst + at, src + at, (size_t)(limit - at), kind, st);
+  }
+  return cudaSuccess;
+}
+
+/* Blocks [b0, b1) of one stream in SEGMENT mode (b0 on a segment boundary) from interleaved samples [b0*spb,
+ * min(b1*spb, ns)): the shard copies only its own samples, encodes its segments as independent chains and writes its
+ * own byte range of the caller's stream (the 31-byte file header with block 0).  Every segment is a chain of its own,
+ * so the pipeline is cut ACROSS the segments: slice j = blocks [j*m, (j+1)*m) of EVERY segment of the shard, which
+ * keeps every chain busy in every launch while slice j+1 is on its way up and slice j-1 on its way down (rows of the
+ * 2-D copies = segments; the chain state crosses the launches in the device state array). */
 static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struct AADEncodeParameter *prm, uint32_t segment_blocks,
                                         const int16_t *interleaved, uint32_t num_samples, uint32_t b0, uint32_t b1,
                                         uint8_t *data)
@@ -1789,10 +1913,10 @@ static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struc
   struct aadf_geometry geo;
   const AADApiResult r = check_encode_shape(prm, num_samples, &geo);
   if (r != AAD_APIRESULT_OK) return r;
-  const uint32_t C = geo.channels, spb = geo.samples_per_block, bs = geo.block_size, ns = num_samples;
+  const uint32_t C = geo.channels, spb = geo.samples_per_block, bs = geo.block_size, ns = num_samples, SB = segment_blocks;
   const uint32_t nblk = aadf_num_blocks(ns, spb);
   const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < ns) ? (uint64_t)b1 * spb : ns;
-  if (b1 <= b0 || s1 <= s0) return AAD_APIRESULT_OK;
+  if (b1 <= b0 || s1 <= s0 || SB == 0 || b0 % SB != 0) return (b1 <= b0 || s1 <= s0) ? AAD_APIRESULT_OK : AAD_APIRESULT_INVALID_ARGUMENT;
   CU(cudaSetDevice(gpu->device), "cudaSetDevice");
   const uint64_t count = s1 - s0;
   const uint64_t pitch = round_up64(count, 64);
@@ -1801,23 +1925,16 @@ static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struc
   uint64_t byte1 = AADF_FILE_HEADER_BYTES + (uint64_t)b1 * bs;
   if (byte1 > total) byte1 = total;
   const uint64_t span = byte1 - byte0;
+  const uint32_t nseg_all = (nblk + SB - 1) / SB;
+  const uint32_t g0 = b0 / SB, g1 = (b1 + SB - 1) / SB, rows = g1 - g0;
+  const size_t state_bytes = (size_t)nseg_all * C * AADK_STATE_WORDS * 4;
   if (!aadgpu_reserve(gpu, &gpu->wav, (size_t)C * count * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->pcm, (size_t)C * pitch * 2)) return AAD_APIRESULT_NG;
   if (!aadgpu_reserve(gpu, &gpu->aad, (size_t)span + (size_t)bs + 256)) return AAD_APIRESULT_NG;
+  if (!aadgpu_reserve(gpu, &gpu->state, state_bytes)) return AAD_APIRESULT_NG;
   cudaStream_t s = gpu->s_run;
-  /* the shard's samples come up in pieces, each de-interleaved while the next is on the link */
-  const uint32_t pieces = pick_stream_slices(count * C * 2, count);
-  for (uint32_t k = 0; k < pieces; k++) {
-    const uint64_t a = count * k / pieces, b = count * (k + 1) / pieces;
-    if (b == a) continue;
-    CU(cudaMemcpyAsync((int16_t *)gpu->wav.ptr + a * C, interleaved + (s0 + a) * C, (size_t)(b - a) * C * 2, cudaMemcpyHostToDevice,
-                       gpu->s_in), "H2D wav shard");
-    CU(cudaEventRecord(gpu->ev_in[k], gpu->s_in), "event");
-    CU(cudaStreamWaitEvent(s, gpu->ev_in[k], 0), "wait");
-    CU((cudaError_t)aadk_launch_deinterleave16((const int16_t *)gpu->wav.ptr + a * C, (int16_t *)gpu->pcm.ptr + a, pitch, C,
-                                               (uint32_t)(b - a), s), "deinterleave kernel launch");
-  }
   CU(cudaMemsetAsync(gpu->aad.ptr, 0, (size_t)span + (size_t)bs + 256, s), "memset aad");
+  CU(cudaMemsetAsync(gpu->state.ptr, 0, state_bytes, s), "memset state");
   /* the shard's first block 32-byte aligned at ptr + 32, the file header (shard 0 only) right in front of it; the
    * kernel is told which byte of the stream and which sample of the rows its buffers start at */
   uint8_t *d_block0 = (uint8_t *)gpu->aad.ptr + 32;
@@ -1836,13 +1953,42 @@ static AADApiResult encode_stream_range_unlocked(struct AADGpu *gpu, const struc
   p.aad = d_block0 - lead;
   p.byte_base = byte0 - lead;
   p.aad_stride = 0;
-  p.block_begin = b0;
-  p.block_end = b1;
-  p.segment_blocks = segment_blocks;
-  p.num_segments = (nblk + segment_blocks - 1) / segment_blocks;
-  CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
-  CU(cudaMemcpyAsync(data + byte0 - lead, d_block0 - lead, (size_t)(span + lead), cudaMemcpyDeviceToHost, s), "D2H aad shard");
-  CU(cudaStreamSynchronize(s), "sync");
+  p.state_in = (const int32_t *)gpu->state.ptr;
+  p.state_out = (int32_t *)gpu->state.ptr;
+  p.segment_blocks = SB;
+  p.num_segments = nseg_all;
+  p.segment_relative = 1;
+  p.segment_begin = g0;
+  p.segment_end = g1;
+
+  /* slices across the segments: about 8 MiB of samples each, at most one per block of a segment */
+  uint32_t slices = pick_stream_slices(count * C * 2, SB);
+  if (slices > 8) slices = 8;                                      /* rows of the 2-D copies stay tens of KiB long */
+  const uint32_t m = (SB + slices - 1) / slices;
+  slices = (SB + m - 1) / m;
+  const uint64_t frame = (uint64_t)C * 2;                          /* bytes per interleaved frame */
+  const uint8_t *h_wav = (const uint8_t *)(interleaved + s0 * C);  /* the shard's samples: frame 0 = sample s0 */
+  uint8_t *d_wav = (uint8_t *)gpu->wav.ptr;
+  uint8_t *h_aad = data + byte0;                                   /* the shard's bytes: offset 0 = block b0 */
+  for (uint32_t j = 0; j < slices; j++) {
+    const uint32_t r0 = j * m, r1 = (r0 + m < SB) ? r0 + m : SB;   /* blocks [r0, r1) of every segment */
+    CU(copy_slice_rows(d_wav, h_wav, (uint64_t)r0 * spb * frame, (uint64_t)SB * spb * frame, (uint64_t)(r1 - r0) * spb * frame, rows,
+                       count * frame, cudaMemcpyHostToDevice, gpu->s_in), "H2D wav slice");
+    CU(cudaEventRecord(gpu->ev_in[j], gpu->s_in), "event");
+    CU(cudaStreamWaitEvent(s, gpu->ev_in[j], 0), "wait");
+    CU((cudaError_t)aadk_launch_deinterleave16_rows((const int16_t *)d_wav, (int16_t *)gpu->pcm.ptr, pitch, C, (uint64_t)SB * spb,
+                                                    (uint64_t)r0 * spb, (r1 - r0) * spb, rows, count, s), "deinterleave kernel launch");
+    p.block_begin = r0;
+    p.block_end = r1;
+    CU((cudaError_t)aadk_launch_encode(&p, s), "encode kernel launch");
+    CU(cudaEventRecord(gpu->ev_run[j], s), "event");
+    CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[j], 0), "wait");
+    if (j == 0 && lead)
+      CU(cudaMemcpyAsync(data, d_block0 - lead, (size_t)lead, cudaMemcpyDeviceToHost, gpu->s_out), "D2H file header");
+    CU(copy_slice_rows(h_aad, d_block0, (uint64_t)r0 * bs, (uint64_t)SB * bs, (uint64_t)(r1 - r0) * bs, rows, span,
+                       cudaMemcpyDeviceToHost, gpu->s_out), "D2H aad slice");
+  }
+  CU(cudaStreamSynchronize(gpu->s_out), "sync");
   return AAD_APIRESULT_OK;
 }
 

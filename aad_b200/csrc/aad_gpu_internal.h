@@ -7,6 +7,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <pthread.h>
+#include <sched.h>
 #include <cuda_runtime_api.h>
 
 #include "aad_b200.h"
@@ -34,6 +35,8 @@ struct AADGpu {
   void *ring_in[3], *ring_out[3];   /* pinned bounce buffers of the drop-in paths (caller memory is pageable), lazily allocated */
   struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2, raw, stats;
   int lut_ready;
+  int cpus_known, cpus_count;       /* AADGpu_BindHostThread: the device's local CPU list, read from sysfs once */
+  cpu_set_t cpus;
   uint32_t segment_blocks;   /* AADGpu_SetEncodeSegmentBlocks; 0 = the reference's whole-stream state carry */
 };
 

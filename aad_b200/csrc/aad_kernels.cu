@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "aad_format.h"
 #include "aad_kernels.h"
@@ -33,6 +34,71 @@ std::atomic<int> g_force_generic{0};   /* tests: route everything through the ge
 std::atomic<int> g_dec_wide_all{0};    /* tests: mono / stereo decode through the any-channel-count staged kernel too */
 std::atomic<int> g_dec_bulk{0};        /* measurement: 1 = mono 4-bit flushes through the TMA unit (cp.async.bulk): measured slower, off */
 std::atomic<int> g_enc_schedule{1};    /* tests / measurement: the encoder's pass schedule, aad_encode_roles.cuh: enc_fast_launch */
+
+/* Launch-shape facts that never change for one (kernel, device): the SM count, the resident CTAs per SM for a block
+ * size and shared-memory size, "the dynamic shared-memory limit of this kernel has been raised to N".  Asking the
+ * runtime on every launch costs several API calls, and API calls of the threads of one process queue up behind
+ * each other -- a device group decoding one stream in 8 shards of ~10 slices each spent more time there than on
+ * the link.  Remembered after the first launch instead. */
+struct LaunchFact {
+  const void *fn;
+  int dev, kind;
+  size_t arg;
+  int value;
+};
+LaunchFact g_facts[256];
+int g_num_facts = 0;
+std::mutex g_facts_lock;
+
+template <typename F>
+int launch_fact(const void *fn, int dev, int kind, size_t arg, int *out, F compute)
+{
+  {
+    std::lock_guard<std::mutex> hold(g_facts_lock);
+    for (int i = 0; i < g_num_facts; i++)
+      if (g_facts[i].fn == fn && g_facts[i].dev == dev && g_facts[i].kind == kind && g_facts[i].arg == arg) {
+        *out = g_facts[i].value;
+        return 0;
+      }
+  }
+  int v = 0;
+  const int rc = compute(&v);
+  if (rc != 0) return rc;
+  {
+    std::lock_guard<std::mutex> hold(g_facts_lock);
+    if (g_num_facts < (int)(sizeof(g_facts) / sizeof(g_facts[0]))) g_facts[g_num_facts++] = LaunchFact{fn, dev, kind, arg, v};
+  }
+  *out = v;
+  return 0;
+}
+
+inline int device_sm_count(int *dev_out, int *sms)
+{
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  *dev_out = dev;
+  return launch_fact(nullptr, dev, 0, 0, sms, [&](int *v) { return (int)cudaDeviceGetAttribute(v, cudaDevAttrMultiProcessorCount, dev); });
+}
+
+/* resident CTAs per SM of `kernel` at this block size and dynamic shared-memory size */
+template <typename K>
+int resident_ctas(K kernel, int dev, int block, size_t smem, int *per_sm)
+{
+  return launch_fact((const void *)kernel, dev, 1, ((size_t)block << 40) | smem, per_sm,
+                     [&](int *v) { return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(v, kernel, block, smem); });
+}
+
+/* cudaFuncAttributeMaxDynamicSharedMemorySize >= smem for `kernel` on this device (per device: a process may drive several) */
+template <typename K>
+int allow_dynamic_smem(K kernel, int dev, size_t smem)
+{
+  int unused = 0;
+  return launch_fact((const void *)kernel, dev, 2, smem, &unused, [&](int *v) {
+    *v = 1;
+    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+}
 
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -327,6 +393,7 @@ __global__ void __launch_bounds__(128) aad_encode_generic(const aadk_encode_para
   const uint32_t seg_first = p.segment_blocks ? seg * p.segment_blocks : 0u;
   const uint32_t seg_end = p.segment_blocks ? seg_first + p.segment_blocks : 0xFFFFFFFFu;
   const uint32_t rel = (p.segment_blocks && p.segment_relative) ? seg_first : 0u;   /* aad_kernels.h: segment_relative */
+  if (p.segment_blocks && p.segment_relative && p.segment_end != 0u && (seg < p.segment_begin || seg >= p.segment_end)) return;
   const uint32_t nblk = min(min(aadf_num_blocks(ns, spb), (uint32_t)min((uint64_t)rel + p.block_end, (uint64_t)0xFFFFFFFFu)), seg_end);
   const uint32_t b_begin = max(rel + p.block_begin, seg_first);
   if (p.segment_blocks && b_begin == seg_first) {
@@ -432,6 +499,21 @@ __global__ void aad_deinterleave16(const int16_t *__restrict__ in, int16_t *__re
   if (t >= (uint64_t)channels * num_samples) return;
   const uint32_t s = (uint32_t)(t / channels), c = (uint32_t)(t % channels);
   out[(uint64_t)c * ch_stride + s] = in[t];
+}
+
+/* the same for `rows` runs of `width` frames, run r starting at frame r * row_frames + first (a within-segment slice
+ * of every segment of a stream); frames at or past `limit` do not exist */
+__global__ void aad_deinterleave16_rows(const int16_t *__restrict__ in, int16_t *__restrict__ out, uint64_t ch_stride,
+                                        uint32_t channels, uint64_t row_frames, uint64_t first, uint32_t width, uint32_t rows,
+                                        uint64_t limit)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t per_row = (uint64_t)width * channels;
+  if (t >= per_row * rows) return;
+  const uint64_t r = t / per_row, k = t % per_row;
+  const uint64_t s = r * row_frames + first + k / channels;
+  const uint32_t c = (uint32_t)(k % channels);
+  if (s < limit) out[(uint64_t)c * ch_stride + s] = in[s * channels + c];
 }
 
 __global__ void aad_interleave16(const int16_t *__restrict__ in, uint64_t ch_stride, int16_t *__restrict__ out,
@@ -657,6 +739,17 @@ int aadk_launch_deinterleave16(const int16_t *interleaved, int16_t *planar, uint
   if (n == 0) return 0;
   aad_deinterleave16<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(interleaved, planar, ch_stride, channels,
                                                                          num_samples);
+  g_launches++;
+  return (int)cudaGetLastError();
+}
+
+int aadk_launch_deinterleave16_rows(const int16_t *interleaved, int16_t *planar, uint64_t ch_stride, uint32_t channels,
+                                    uint64_t row_frames, uint64_t first, uint32_t width, uint32_t rows, uint64_t limit, void *stream)
+{
+  const uint64_t n = (uint64_t)channels * width * rows;
+  if (n == 0) return 0;
+  aad_deinterleave16_rows<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(interleaved, planar, ch_stride, channels, row_frames,
+                                                                              first, width, rows, limit);
   g_launches++;
   return (int)cudaGetLastError();
 }

@@ -77,6 +77,10 @@ struct aadk_encode_params {
    * [block_begin, block_end) of each segment are encoded), so a host pipeline can cut a stream of many short
    * chains into slices that keep every chain busy */
   uint32_t segment_relative;
+  /* with segment_relative: only segments [segment_begin, segment_end) take part (a device's shard of one stream);
+   * segment_end == 0 means all of them */
+  uint32_t segment_begin;
+  uint32_t segment_end;
   /* shards of one stream: `aad` points at byte byte_base of every stream, the rows of `pcm` start at sample
    * sample_base (see aadk_decode_params) */
   uint64_t byte_base;
@@ -106,6 +110,10 @@ int aadk_launch_deinterleave16(const int16_t *interleaved, int16_t *planar, uint
                                uint32_t num_samples, void *stream);
 int aadk_launch_interleave16(const int16_t *planar, uint64_t ch_stride, int16_t *interleaved, uint32_t channels,
                              uint32_t num_samples, void *stream);
+/* de-interleave `rows` runs of `width` frames, run r starting at frame r * row_frames + first of the (whole-stream)
+ * interleaved / planar buffers; frames at or past `limit` are skipped */
+int aadk_launch_deinterleave16_rows(const int16_t *interleaved, int16_t *planar, uint64_t ch_stride, uint32_t channels,
+                                    uint64_t row_frames, uint64_t first, uint32_t width, uint32_t rows, uint64_t limit, void *stream);
 
 /* planar int32 rows (the reference API's sample type, int16-range values) <-> planar int16 rows;
  * pitches in elements; widen converts elements [first, first + n) of every row */

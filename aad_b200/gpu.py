@@ -38,7 +38,7 @@ class GpuApi:
         "AADGpu_EncodeInterleaved16", "AADGpu_DecodeInterleaved16", "AADGpu_ReconstructInterleaved16", "AADGpu_AnalyzeWav", "AADGpu_EncodeWav",
         "AADGpuGroup_Create", "AADGpuGroup_Destroy", "AADGpuGroup_Size", "AADGpuGroup_Device",
         "AADGpuGroup_EncodeBatch", "AADGpuGroup_DecodeBatch", "AADGpuGroup_DecodeInterleaved16",
-        "AADGpuGroup_EncodeInterleaved16", "AADGpu_LinkProbe",
+        "AADGpuGroup_EncodeInterleaved16", "AADGpu_LinkProbe", "AADGpu_LinkProbeRows", "AADGpu_CopyProbeBatch",
     )
 
     def __init__(self, lib):
@@ -86,6 +86,8 @@ class GpuApi:
             "AADGpuGroup_DecodeInterleaved16": (C.c_int, [vp, vp, u32, vp, u32]),
             "AADGpuGroup_EncodeInterleaved16": (C.c_int, [vp, pp, u32, vp, u32, vp, u32, C.POINTER(u32)]),
             "AADGpu_LinkProbe": (C.c_int, [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+            "AADGpu_CopyProbeBatch": (C.c_int, [vp, bp, vp, vp, vp]),
+            "AADGpu_LinkProbeRows": (C.c_int, [vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)

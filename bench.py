@@ -607,12 +607,18 @@ def run_b200_arm(args):
         barrier()
         check(gpu.lib.AADGpu_LinkProbe(ctx, 2 << 30, 2, gbs), "link probe")
         mine = torch.tensor([gbs[0], gbs[1], gbs[2]], dtype=torch.float64, device=dev)
-        total = mine.clone()
+        every = [torch.zeros_like(mine) for _ in range(world)]
         if world > 1:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+            dist.all_gather(every, mine)
+        else:
+            every = [mine]
+        every = torch.stack(every).cpu()           # [rank][h2d, d2h, both]
         link = {"h2d": round(gbs[0], 2), "d2h": round(gbs[1], 2), "both": round(gbs[2], 2),
-                "sum_over_ranks": {k: round(float(v), 2) for k, v in zip(("h2d", "d2h", "both"), total.cpu())},
-                "what": "pinned 1-D 2 GiB copies, all ranks at the same time (AADGpu_LinkProbe); rank 0's own rates first"}
+                "sum_over_ranks": {k: round(float(every[:, i].sum()), 2) for i, k in enumerate(("h2d", "d2h", "both"))},
+                "slowest_rank": {k: round(float(every[:, i].min()), 2) for i, k in enumerate(("h2d", "d2h", "both"))},
+                "per_rank_both": [round(float(x), 1) for x in every[:, 2]],
+                "what": "pinned 1-D 2 GiB copies, all ranks at the same time (AADGpu_LinkProbe); rank 0's own rates first; "
+                        "bursts of 4 GiB per direction -- the sustained figure for the e2e traffic is e2e.copies_only"}
 
     # ---- end to end through the host C ABI, pinned host buffers ------------------------------------
     e2e = None
@@ -651,6 +657,9 @@ def run_b200_arm(args):
             check(gpu.lib.AADGpu_ReconstructBatch(ctx, C.byref(hb), h_pcm.ctypes.data, None, h_aad.ctypes.data, None,
                                                   h_out.ctypes.data), "e2e round trip")
 
+        def copies_only():     # the same host <-> device copies with no kernel between them: the floor on this box
+            check(gpu.lib.AADGpu_CopyProbeBatch(ctx, C.byref(hb), h_pcm.ctypes.data, h_aad.ctypes.data, h_out.ctypes.data), "copy probe")
+
         def timed(fn):
             """-> (seconds per step as max over ranks, results equal to the device-resident ones)"""
             h_aad[...] = 0
@@ -677,7 +686,10 @@ def run_b200_arm(args):
         pcm_bytes, aad_bytes = Ne * ch * n * 2, Ne * astride
         s2, same2 = timed(two_calls)
         s1, same1 = timed(one_call)
-        same = torch.tensor([int(same1), int(same2)], dtype=torch.int32, device=dev)
+        check(gpu.lib.AADGpu_ReconstructBatch(ctx, C.byref(hb), h_pcm.ctypes.data, None, h_aad.ctypes.data, None, h_out.ctypes.data),
+              "e2e round trip")                       # leaves the device buffers holding the results the probe copies down
+        s0, same0 = timed(copies_only)
+        same = torch.tensor([int(same1 and same0), int(same2)], dtype=torch.int32, device=dev)
         if world > 1:
             dist.all_reduce(same, op=dist.ReduceOp.MIN)
         same1, same2 = (bool(x) for x in same.cpu())
@@ -689,7 +701,13 @@ def run_b200_arm(args):
                "steps": e2e_steps, "ms_per_step": round(s1 * 1e3, 3), "clips_per_gpu": Ne,
                "matches_device_resident_result": same1, "host_cpus_bound": int(local_cpus),
                "host_traffic_gbs_all_ranks": round(moved_gbs, 2), "link_probe_gbs": link,
-               "frac_of_link": round(moved_gbs / link["sum_over_ranks"]["both"], 4) if link else None,
+               "copies_only": {"ms_per_step": round(s0 * 1e3, 3),
+                               "host_traffic_gbs_all_ranks": round(total_clips * (2 * ch * n * 2 + astride) / s0 / 1e9, 2),
+                               "what": "AADGpu_CopyProbeBatch: exactly this call's host <-> device copies (same pinned buffers, slices "
+                                       "and row shapes, both directions at once, every rank at the same time), no kernels: the "
+                                       "floor of the end-to-end call on this box, max over ranks"},
+               "frac_of_link": round(s0 / s1, 4),
+               "frac_of_probe_sum": round(moved_gbs / link["sum_over_ranks"]["both"], 4) if link else None,
                "path": "AADGpu_ReconstructBatch (host C ABI, pinned host buffers; per slice H2D pcm | encode | decode | "
                        "D2H .aad + pcm, both link directions busy at once)",
                "separate_calls": {"value": round(total_samples / s2 / 1e6, 3), "ms_per_step": round(s2 * 1e3, 3),

@@ -90,6 +90,9 @@ int AADGpu_BindHostThread(struct AADGpu *gpu);
  * (aggregate), in GB/s.  What the pipelined entry points below can at best reach; bench.py reports it beside
  * their end-to-end figures. */
 AADApiResult AADGpu_LinkProbe(struct AADGpu *gpu, size_t bytes, int repeats, double gbs[3]);
+/* the same for `rows` rows of `width` bytes that lie `host_pitch` bytes apart in pinned host memory (packed on the
+ * device): the shape of the copies the batch pipelines issue -- a block-range slice of every stream of a batch */
+AADApiResult AADGpu_LinkProbeRows(struct AADGpu *gpu, size_t rows, size_t width, size_t host_pitch, int repeats, double gbs[3]);
 
 /* pinned host memory for the host entry points (plain malloc'd memory works too, slower) */
 void *AADGpu_HostAlloc(size_t bytes);
@@ -129,6 +132,13 @@ AADApiResult AADGpu_DecodeBatch(struct AADGpu *gpu, const struct AADGpuBatch *ba
 AADApiResult AADGpu_ReconstructBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch,
                                      const int16_t *pcm, const uint32_t *num_samples,
                                      uint8_t *aad, uint32_t *out_sizes, int16_t *reconstructed);
+
+/* Measurement: exactly the host <-> device copies AADGpu_ReconstructBatch issues for this batch and these buffers
+ * (same slices, row shapes and streams), without the kernels and without any dependency between the copies -- the
+ * time the end-to-end call cannot beat on this box.  Call it right after AADGpu_ReconstructBatch on the same
+ * arguments: the device buffers still hold that call's results, so `aad` and `reconstructed` receive the same bytes. */
+AADApiResult AADGpu_CopyProbeBatch(struct AADGpu *gpu, const struct AADGpuBatch *batch, const int16_t *pcm, uint8_t *aad,
+                                   int16_t *reconstructed);
 
 /* ---- one stream in WAV order (interleaved int16), host pointers: what `aad -e / -d / -r` call ---- */
 /* src/main.c:141-227 (execute_encode) without the host-side int32 shuffle: the 16-bit samples of a
