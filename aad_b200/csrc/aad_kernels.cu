@@ -89,15 +89,22 @@ int resident_ctas(K kernel, int dev, int block, size_t smem, int *per_sm)
                      [&](int *v) { return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(v, kernel, block, smem); });
 }
 
-/* cudaFuncAttributeMaxDynamicSharedMemorySize >= smem for `kernel` on this device (per device: a process may drive several) */
+/* cudaFuncAttributeMaxDynamicSharedMemorySize >= smem for `kernel` on this device (per device: a process may drive
+ * several).  The attribute is ONE value per kernel, so what is remembered is the largest size granted so far: a
+ * launch that needs less is fine as it is, one that needs more raises the limit. */
 template <typename K>
 int allow_dynamic_smem(K kernel, int dev, size_t smem)
 {
-  int unused = 0;
-  return launch_fact((const void *)kernel, dev, 2, smem, &unused, [&](int *v) {
-    *v = 1;
-    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  std::lock_guard<std::mutex> hold(g_facts_lock);
+  LaunchFact *slot = nullptr;
+  for (int i = 0; i < g_num_facts && !slot; i++)
+    if (g_facts[i].fn == (const void *)kernel && g_facts[i].dev == dev && g_facts[i].kind == 2) slot = &g_facts[i];
+  if (slot && slot->arg >= smem) return 0;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if (!slot && g_num_facts < (int)(sizeof(g_facts) / sizeof(g_facts[0]))) slot = &g_facts[g_num_facts++];
+  if (slot) *slot = LaunchFact{(const void *)kernel, dev, 2, smem, 1};
+  return 0;
 }
 
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
