@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(512) k(int *out, int a0, int b0, unsigned long
       if (OP == 21) asm volatile("sub.s32 %0, %1, %0;" : "+r"(r[j]) : "r"(b));
       if (OP == 22) asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[j]));
       if (OP == 23) asm volatile("abs.s32 %0, %0;" : "+r"(r[j]));
+      if (OP == 24) asm volatile("{.reg .s16 h; cvt.sat.s16.s32 h, %0; cvt.s32.s16 %0, h;}" : "+r"(r[j]));          // 16-bit clip in one op?
+      if (OP == 25) { asm volatile("{.reg .s16 h; cvt.sat.s16.s32 h, %0; cvt.s32.s16 %0, h;}" : "+r"(r[j])); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[(j + 4) & 7]) : "r"(b), "r"(c)); }
+      if (OP == 26) { asm volatile("{.reg .s16 h; cvt.sat.s16.s32 h, %0; cvt.s32.s16 %0, h;}" : "+r"(r[j])); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[(j + 4) & 7]) : "r"(b), "r"(c)); }
+      if (OP == 27) { asm volatile("min.s32 %0, %0, %1;" : "+r"(r[j]) : "r"(b)); asm volatile("max.s32 %0, %0, %1;" : "+r"(r[j]) : "r"(c)); }
     }
   }
   long long t1 = clock64();
@@ -98,6 +102,10 @@ int main()
     run<22>("I2F", 1, threads);
     run<10>("LDS random (dependent)", 1, threads);
     run<11>("LDS conflict-free (dependent)", 1, threads);
+    run<24>("cvt.sat.s16.s32 (clip16)", 1, threads);
+    run<25>("clip16 cvt + LOP3 interleaved", 2, threads);
+    run<26>("clip16 cvt + IMAD interleaved", 2, threads);
+    run<27>("min + max (clip16 as today)", 2, threads);
     run<12>("IMAD + LOP3 interleaved", 2, threads);
     run<20>("2 IMAD + 1 LOP3 interleaved", 3, threads);
   }
