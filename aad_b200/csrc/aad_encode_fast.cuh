@@ -12,9 +12,12 @@
  * carried state, run interleaved in the same thread (enc_run_pair).
  *
  * What makes a pass fast:
- *  - no integer divide: floor((|diff| << (b-2)) / step) is umulhi(|diff| << (b-1), M[step]) >> L[step]
- *    with a per-step magic pair, exact for every reachable operand (tools/gen_tables.py);
- *  - one 8-byte shared-memory load per sample fetches {step, L, M} from a table indexed directly
+ *  - no integer divide and no shift around it: min((|diff| << (b-2)) / step, 2^(b-1) - 1) is
+ *    min(umulhi(|diff|, D[step]), 2^(b-1) - 1) with D = ceil(2^(30+b) / step), exact wherever the clamp does
+ *    not hide the quotient (tools/gen_tables.py).  D does not fit 32 bits for the first few steps
+ *    (step <= 2^(b-2): "tiny" rows, near-silent signals): a 16-sample unit that could reach them takes the
+ *    SAFE copy of the loop, which pre-shifts the operand there (EncQuant);
+ *  - one 8-byte shared-memory load per sample fetches {step, D} from a table indexed directly
  *    by the Q4 step index (kept pre-multiplied by 8 in a register), the index update is one
  *    VIADDMNMX.RELU, the index-delta table is a register-resident byte LUT (3 PRMT);
  *  - short recurrence: |x - p| is one VABSDIFF, the sign of the difference is folded into the
@@ -39,7 +42,7 @@ namespace {
 
 constexpr int kEncLutEntries = AADF_INDEX_MAX + 1;
 
-typedef uint2 EncLutEntry;     /* x = (step << 16) | shift, y = magic */
+typedef uint2 EncLutEntry;     /* x = (step << 16) | tiny, y = D (tiny rows: ceil(2^31 / step)) */
 struct EncShared {
   EncLutEntry lut[kEncLutEntries];   /* indexed by stepsize_index */
 };
@@ -73,15 +76,25 @@ struct EncDelta {
   }
 };
 
-__device__ const uint32_t g_step_magic[256] = AADK_STEP_MAGIC_INIT;
-__device__ const uint8_t g_step_shift[256] = AADK_STEP_SHIFT_INIT;
+__device__ const uint32_t g_step_direct[3][256] = {AADK_STEP_DIRECT2_INIT, AADK_STEP_DIRECT3_INIT, AADK_STEP_DIRECT4_INIT};
+
+/* The shift-free quantiser (tools/gen_tables.py): rows [0, kTinyRows) of the step table need the operand pre-shifted
+ * by b-1.  A 16-sample unit may use the copy of the loop without that (SAFE = 0) when the step index cannot come down
+ * to a tiny row before the unit's last table lookup: index >= kFastIndex at its start (the index falls by at most
+ * kMaxDrop per sample, src/aad_tables.c:8-45). */
+template <int BITS>
+struct EncQuant {
+  static constexpr int kTinyRows = (BITS == 4) ? AADK_TINY_ROWS4 : (BITS == 3 ? AADK_TINY_ROWS3 : AADK_TINY_ROWS2);
+  static constexpr int kMaxDrop = (BITS == 4) ? 18 : (BITS == 3 ? 16 : 14);
+  static constexpr int kFastIndex = 16 * kTinyRows - 8 + 16 * kMaxDrop;   /* units are 16 samples (kEncUnit) */
+};
 
 template <int BITS>
 __device__ __forceinline__ void enc_load_shared(EncShared &s)
 {
   for (int i = threadIdx.x; i < kEncLutEntries; i += blockDim.x) {
     const int e = (i + 8) >> 4;
-    s.lut[i] = make_uint2(((uint32_t)g_step_table[e] << 16) | g_step_shift[e], g_step_magic[e]);
+    s.lut[i] = make_uint2(((uint32_t)g_step_table[e] << 16) | (e < EncQuant<BITS>::kTinyRows ? 1u : 0u), g_step_direct[BITS - 2][e]);
   }
   __syncthreads();
 }
@@ -95,17 +108,23 @@ struct EncChain {
   int32_t h0, h1, h2, h3;   /* h0 newest */
   int32_t w0, w1, w2, w3;
   int32_t idx8;             /* kEncIdxScale * stepsize_index */
+  EncLutEntry e;            /* the table entry of idx8, fetched as soon as idx8 is known (prime / the previous sample) */
+  __device__ __forceinline__ void prime(const EncShared &s)
+  {
+    e = *reinterpret_cast<const EncLutEntry *>(reinterpret_cast<const char *>(s.lut) + idx8);
+  }
   __device__ __forceinline__ void set(const EncState &s) { w0 = s.w0; w1 = s.w1; w2 = s.w2; w3 = s.w3; idx8 = s.idx8; }
   __device__ __forceinline__ EncState state() const { return EncState{w0, w1, w2, w3, idx8}; }
 };
 
-/* src/aad_encoder.c:343-410, one sample.  Returns the magnitude|sign code; q = signed dequantised diff. */
-template <int BITS>
+/* src/aad_encoder.c:343-410, one sample.  Returns the magnitude|sign code; q = signed dequantised diff.
+ * SAFE = 0 only where the step index is known to stay clear of the tiny rows (EncQuant). */
+template <int BITS, int SAFE = 1>
 __device__ __forceinline__ uint32_t enc_sample(EncChain &c, int32_t x, const EncShared &s, int32_t &q)
 {
   constexpr uint32_t kMaxMag = (1u << (BITS - 1)) - 1u;
   constexpr int kSh = BITS - 1;
-  const EncLutEntry e = *reinterpret_cast<const EncLutEntry *>(reinterpret_cast<const char *>(s.lut) + c.idx8);
+  const EncLutEntry e = c.e;
   const int32_t step = (int32_t)(e.x >> 16), step2 = 2 * step;
   /* predictor: two independent multiply-add chains, joined by one add */
   int32_t acc_a, acc_b;   /* asm keeps the two chains apart (the compiler would re-serialise them) */
@@ -117,9 +136,9 @@ __device__ __forceinline__ uint32_t enc_sample(EncChain &c, int32_t x, const Enc
   /* |x| <= 2^15 and |p| <= 2^16: the difference cannot wrap, so sign and magnitude come from
    * a compare and a VABSDIFF instead of subtract + abs */
   const bool neg = x < p;
-  const uint32_t a = __sad(x, p, 0u);
-  uint32_t mag = __funnelshift_r(__umulhi(a << kSh, e.y), 0u, e.x);   /* >> (e.x & 31) */
-  mag = min(mag, kMaxMag);
+  uint32_t a = __sad(x, p, 0u);
+  if (SAFE) a = (e.x & 1u) ? a << kSh : a;
+  const uint32_t mag = min(__umulhi(a, e.y), kMaxMag);
   /* q = +-((step * (2 mag + 1)) >> kSh): for the negative branch -(v >> k) == (-v + 2^k - 1) >> k,
    * so the sign goes into the multiplier and the addend, both ready before mag is */
   const int32_t s2 = neg ? -step2 : step2;
@@ -131,6 +150,7 @@ __device__ __forceinline__ uint32_t enc_sample(EncChain &c, int32_t x, const Enc
   c.w2 += (int32_t)((uint32_t)q * (uint32_t)c.h2 + (1u << 14)) >> 18;
   c.w3 += (int32_t)((uint32_t)q * (uint32_t)c.h3 + (1u << 14)) >> 18;
   c.idx8 = __viaddmin_s32_relu(c.idx8, EncDelta<BITS>::lookup(mag), kEncIdxScale * AADF_INDEX_MAX);
+  c.prime(s);   /* the next sample's entry: its latency overlaps the rest of this sample, also across units */
   c.h3 = c.h2;
   c.h2 = c.h1;
   c.h1 = c.h0;
@@ -321,7 +341,7 @@ struct EncJob {
 };
 
 template <int BITS, int MS>
-__device__ __forceinline__ void enc_job_begin(EncJob<MS> &j, const EncSource<MS> &src, uint32_t ch, uint32_t C)
+__device__ __forceinline__ void enc_job_begin(EncJob<MS> &j, const EncSource<MS> &src, uint32_t ch, uint32_t C, const EncShared &sh)
 {
   constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
   j.sum = 0.0;
@@ -331,6 +351,7 @@ __device__ __forceinline__ void enc_job_begin(EncJob<MS> &j, const EncSource<MS>
   j.bytes.begin(j.dp);
   if (!j.run) return;
   EncChain &c = j.c;
+  c.prime(sh);
   enc_load_history<MS>(c, src, j.first, j.n);
   if (j.emit) {   /* block header, src/aad_encoder.c:619-655 */
     int32_t maxabs = 0;
@@ -397,28 +418,39 @@ __device__ __forceinline__ void enc_job_put_unit(EncJob<MS> &j, const uint32_t h
   }
 }
 
-/* the full 16-sample units [u0, units) of one job.  KIND 0: dry run (error sum only), 1: emitting
- * (codes only): two copies of the loop, 3 instructions per sample shorter each than one that does both */
+/* one full 16-sample unit u of a job: wait for its samples, request the unit kEncAhead further on, run the 16 samples.
+ * KIND 0: dry run (error sum only), 1: emitting (codes only): two copies of the loop, 3 instructions per sample
+ * shorter each than one that does both.  SAFE: see EncQuant.  The whole unit is ONE basic block on purpose: the ring
+ * bookkeeping and the next unit's request issue in the stall slots of the sample recurrence. */
+template <int BITS, int MS, int KIND, int SAFE>
+__device__ __forceinline__ void enc_job_unit(EncJob<MS> &j, const EncSource<MS> &src, uint32_t u, bool mono, uint32_t gstride,
+                                             const EncShared &sh)
+{
+  EncChain &c = j.c;
+  EncRing<MS>::template wait<kEncAhead - 1>();
+  EncUnit<MS> cur;
+  cur.read(j.ring, u & (kEncSlots - 1), src);
+  enc_job_request<MS>(j, src, u + kEncAhead);
+  EncRing<MS>::commit();
+  uint32_t half[2] = {0u, 0u};
+#pragma unroll
+  for (int k = 0; k < kEncUnit; k++) {
+    int32_t q;
+    const uint32_t code = enc_sample<BITS, SAFE>(c, cur.get(src, k), sh, q);
+    if (KIND != 0) half[k >> 3] = (half[k >> 3] << BITS) + code;
+    if (KIND != 1) enc_add_square(j.sum, q);
+  }
+  if (KIND == 1) enc_job_put_unit<BITS, MS>(j, half, mono, gstride);
+}
+
+/* the full 16-sample units [u0, units) of one job */
 template <int BITS, int MS, int KIND>
 __device__ __forceinline__ void enc_job_units(EncJob<MS> &j, const EncSource<MS> &src, uint32_t u0, bool mono,
                                               uint32_t gstride, const EncShared &sh)
 {
-  EncChain &c = j.c;
   for (uint32_t u = u0; u < j.units; u++) {
-    EncRing<MS>::template wait<kEncAhead - 1>();
-    EncUnit<MS> cur;
-    cur.read(j.ring, u & (kEncSlots - 1), src);
-    enc_job_request<MS>(j, src, u + kEncAhead);
-    EncRing<MS>::commit();
-    uint32_t half[2] = {0u, 0u};
-#pragma unroll
-    for (int k = 0; k < kEncUnit; k++) {
-      int32_t q;
-      const uint32_t code = enc_sample<BITS>(c, cur.get(src, k), sh, q);
-      if (KIND != 0) half[k >> 3] = (half[k >> 3] << BITS) + code;
-      if (KIND != 1) enc_add_square(j.sum, q);
-    }
-    if (KIND == 1) enc_job_put_unit<BITS, MS>(j, half, mono, gstride);
+    if (j.c.idx8 >= kEncIdxScale * EncQuant<BITS>::kFastIndex) enc_job_unit<BITS, MS, KIND, 0>(j, src, u, mono, gstride, sh);
+    else enc_job_unit<BITS, MS, KIND, 1>(j, src, u, mono, gstride, sh);   /* near silence: the index may reach the tiny rows */
   }
 }
 
@@ -468,13 +500,33 @@ template <int BITS, int MS>
 __device__ __forceinline__ void enc_run_job(EncJob<MS> &j, const EncSource<MS> &src, uint32_t ch, uint32_t C,
                                             const EncShared &sh)
 {
-  enc_job_begin<BITS, MS>(j, src, ch, C);
+  enc_job_begin<BITS, MS>(j, src, ch, C, sh);
 #pragma unroll
   for (int d = 0; d < kEncAhead; d++) {
     enc_job_request<MS>(j, src, d);
     EncRing<MS>::commit();
   }
   enc_job_finish<BITS, MS>(j, src, 0u, C, sh);
+}
+
+/* one 16-sample unit of two DRY passes interleaved instruction by instruction (enc_run_pair) */
+template <int BITS, int MS, int SAFE>
+__device__ __forceinline__ void enc_pair_unit(EncJob<MS> &x, EncJob<MS> &y, const EncSource<MS> &src, uint32_t u, const EncShared &sh)
+{
+  EncRing<MS>::template wait<kEncAhead - 1>();
+  EncUnit<MS> ux, uy;
+  ux.read(x.ring, u & (kEncSlots - 1), src);
+  uy.read(y.ring, u & (kEncSlots - 1), src);
+  enc_job_request<MS>(x, src, u + kEncAhead);
+  enc_job_request<MS>(y, src, u + kEncAhead);
+  EncRing<MS>::commit();
+#pragma unroll
+  for (int k = 0; k < kEncUnit; k++) {
+    int32_t qx, qy;
+    (void)enc_sample<BITS, SAFE>(x.c, ux.get(src, k), sh, qx);
+    (void)enc_sample<BITS, SAFE>(y.c, uy.get(src, k), sh, qy);
+    enc_add_square(x.sum, qx);
+  }
 }
 
 /* Two DRY passes of the same thread at once (the baseline pass and the first trial pass of a block
@@ -487,8 +539,8 @@ template <int BITS, int MS>
 __device__ __forceinline__ void enc_run_pair(EncJob<MS> &x, EncJob<MS> &y, const EncSource<MS> &src, uint32_t ch,
                                              uint32_t C, const EncShared &sh)
 {
-  enc_job_begin<BITS, MS>(x, src, ch, C);
-  enc_job_begin<BITS, MS>(y, src, ch, C);
+  enc_job_begin<BITS, MS>(x, src, ch, C, sh);
+  enc_job_begin<BITS, MS>(y, src, ch, C, sh);
 #pragma unroll
   for (int d = 0; d < kEncAhead; d++) {
     enc_job_request<MS>(x, src, d);
@@ -497,20 +549,8 @@ __device__ __forceinline__ void enc_run_pair(EncJob<MS> &x, EncJob<MS> &y, const
   }
   const uint32_t common = (x.run && y.run) ? min(x.units, y.units) : 0u;
   for (uint32_t u = 0; u < common; u++) {
-    EncRing<MS>::template wait<kEncAhead - 1>();
-    EncUnit<MS> ux, uy;
-    ux.read(x.ring, u & (kEncSlots - 1), src);
-    uy.read(y.ring, u & (kEncSlots - 1), src);
-    enc_job_request<MS>(x, src, u + kEncAhead);
-    enc_job_request<MS>(y, src, u + kEncAhead);
-    EncRing<MS>::commit();
-#pragma unroll
-    for (int k = 0; k < kEncUnit; k++) {
-      int32_t qx, qy;
-      (void)enc_sample<BITS>(x.c, ux.get(src, k), sh, qx);
-      (void)enc_sample<BITS>(y.c, uy.get(src, k), sh, qy);
-      enc_add_square(x.sum, qx);
-    }
+    if (min(x.c.idx8, y.c.idx8) >= kEncIdxScale * EncQuant<BITS>::kFastIndex) enc_pair_unit<BITS, MS, 0>(x, y, src, u, sh);
+    else enc_pair_unit<BITS, MS, 1>(x, y, src, u, sh);
   }
 #pragma unroll 1
   for (int which = 0; which < 2; which++) enc_job_finish<BITS, MS>(which ? y : x, src, common, C, sh);

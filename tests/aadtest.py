@@ -137,9 +137,15 @@ def signal(kind, channels, n, seed=0):
                       + rng.integers(-800, 801, size=n) for c in range(channels)])
     elif kind == "steps":          # slow square between extremes: saturates weights / shift field
         x = np.stack([np.where((t // 37) % 2 == 0, 30000, -30000)] * channels) + rng.integers(-50, 51, size=(channels, n))
+    elif kind == "fades":          # noise whose level sweeps 0 .. loud .. 0 in bursts: the step index walks through
+        level = np.abs(np.sin(np.pi * t / 700.0)) ** 6 * (3.0 ** (seed % 9))   # the first rows of the step table and back
+        x = np.rint(rng.standard_normal((channels, n)) * level).astype(np.int64)
+    elif kind == "whisper":        # +-1 .. +-6 LSB noise with silent gaps: steps 1 .. 8
+        x = rng.integers(-(1 + seed % 6), 2 + seed % 6, size=(channels, n)) * ((t // 53) % 3 != 0)
     else:
         raise ValueError(kind)
     return np.clip(x, -32768, 32767).astype(np.int16)
 
 
 SIGNALS = ("sine", "noise", "nyquist", "silence", "impulse", "music", "steps")
+QUIET_SIGNALS = ("fades", "whisper", "silence", "impulse")

@@ -285,6 +285,32 @@ def test_encoder_schedules_do_not_change_a_byte(product, gpu_ctx, oracle, bits, 
                     assert rc == 0 and res[0][0][i, :res[0][1][i]].tobytes() == want, (n_streams, block, trials, i)
 
 
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_quantiser_near_silence_matches_oracle(product, gpu_ctx, oracle, bits):
+    """The encoder's shift-free quantiser has two copies of the 16-sample loop: one for units whose step index stays
+    clear of the first rows of the step table (steps <= 2^(b-2)), one for units that may reach them (EncQuant in
+    aad_encode_fast.cuh).  Signals that fade into silence and back, +-1..6 LSB noise, silence and an impulse walk
+    the index across that boundary in both directions, in every schedule, mono and stereo."""
+    _, gpu = product
+    for channels, ms in ((1, False), (2, True)):
+        n_streams, n_max = 45, 6100
+        rng = np.random.default_rng(3000 + bits * 10 + channels)
+        lens = rng.integers(200, n_max + 1, size=n_streams).astype(np.uint32)
+        lens[0] = n_max
+        pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+        for i in range(n_streams):
+            pcm[i, :, :lens[i]] = aadtest.signal(aadtest.QUIET_SIGNALS[i % 2 if i < 40 else 2 + i % 2], channels, int(lens[i]), i)
+        for schedule in (1, 0, 2, 3):
+            gpu.lib.AADGpu_SetEncoderSchedule(schedule)
+            try:
+                aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, 1024, ms, 2, num_samples=lens)
+            finally:
+                gpu.lib.AADGpu_SetEncoderSchedule(1)
+            for i in range(n_streams):
+                rc, want = oracle.encode(pcm[i, :, :lens[i]], 44100, bits, 1024, ms, 2)
+                assert rc == 0 and aad[i, :sizes[i]].tobytes() == want, (channels, schedule, i, lens[i])
+
+
 def test_encoder_schedules_carry_state_across_launch_slices(product, gpu_ctx, oracle):
     """AADGpu_EncodeBatch cuts a batch larger than 64 MiB of PCM into block-range slices; the chain state crosses the
     launches through the device state array in every schedule (first-block rules only in the stream's block 0)."""

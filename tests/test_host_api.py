@@ -298,6 +298,31 @@ def test_synth_generator_mirror_is_deterministic(product):
     assert a.dtype == np.int16 and abs(int(a.max())) > 10000
 
 
+def test_shift_free_quantiser_tables_are_exact():
+    """The production quantiser (aad_encode_fast.cuh, enc_sample): min(umulhi(|d|, D), maxmag) for the regular rows and
+    min(umulhi(|d| << (b-1), D), maxmag) for the first AADK_TINY_ROWSb rows equals min((|d| << (b-2)) / step, maxmag)
+    (src/aad_encoder.c:372) for every table step and every reachable |d| (|sample - predict| < 2^17)."""
+    import re
+    text = (ROOT / "aad_b200" / "csrc" / "aad_tables_data.h").read_text().replace("\\\n", " ")
+
+    def table(name):
+        body = re.search(name + r" \{(.*?)\}", text, re.S).group(1)
+        return [int(v.rstrip("u")) for v in re.findall(r"-?\d+u?", body)]
+
+    steps = table("AADK_STEP_TABLE_INIT")
+    d = np.arange(0, 1 << 17, dtype=np.uint64)
+    for bits in (2, 3, 4):
+        direct = table(f"AADK_STEP_DIRECT{bits}_INIT")
+        tiny = int(re.search(rf"#define AADK_TINY_ROWS{bits} (\d+)", text).group(1))
+        assert len(direct) == 256 and all(0 < m < (1 << 32) for m in direct)
+        assert tiny == sum(1 for s in steps if s <= (1 << (bits - 2)))
+        maxmag = (1 << (bits - 1)) - 1
+        for row, (s, m) in enumerate(zip(steps, direct)):
+            operand = d << np.uint64(bits - 1) if row < tiny else d
+            fast = np.minimum((operand * np.uint64(m)) >> np.uint64(32), maxmag)
+            assert np.array_equal(fast, np.minimum((d << np.uint64(bits - 2)) // np.uint64(s), maxmag)), (s, bits)
+
+
 def test_magic_division_tables_are_exact():
     """The encoder's divide-free quantiser: umulhi(|d| << (b-1), M) >> L == (|d| << (b-2)) / step for
     every table step and every reachable |d| (|sample - predict| < 2^17), all bit depths."""
