@@ -193,7 +193,7 @@ template <int MS>
 struct EncRing {
   static constexpr uint32_t kParts = MS ? 4u : 2u;
   static constexpr uint32_t kSlotBytes = kParts * 32u * 16u;
-  static constexpr uint32_t kWarpBytes = kEncSlots * kSlotBytes;
+  static constexpr uint32_t kWarpBytes = (kEncSlots + 1) * kSlotBytes;   /* slot kEncSlots: a pass's last, partial unit */
   uint32_t base;   /* shared-space address of this lane's 16 bytes in slot 0, part 0 */
 
   static __device__ __forceinline__ void cp8(uint32_t dst, const void *src)
@@ -213,6 +213,22 @@ struct EncRing {
       cp8(d + 1032u, src.b + i + 4);
       cp8(d + 1536u, src.b + i + 8);
       cp8(d + 1544u, src.b + i + 12);
+    }
+  }
+  /* the first `pieces` (1..3) 4-sample pieces of the unit that starts at sample i: a pass's last, partial unit */
+  __device__ __forceinline__ void issue_pieces(uint32_t slot, const EncSource<MS> &src, uint32_t i, uint32_t pieces) const
+  {
+    const uint32_t d = base + slot * kSlotBytes;
+    const bool both = MS && src.mode != 0;
+    cp8(d, src.a + i);
+    if (both) cp8(d + 1024u, src.b + i);
+    if (pieces > 1u) {
+      cp8(d + 8u, src.a + i + 4);
+      if (both) cp8(d + 1032u, src.b + i + 4);
+    }
+    if (pieces > 2u) {
+      cp8(d + 512u, src.a + i + 8);
+      if (both) cp8(d + 1536u, src.b + i + 8);
     }
   }
   static __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -335,6 +351,7 @@ struct EncJob {
   double sum;
   /* progress */
   uint32_t units;        /* full 16-sample units after the 4 history samples */
+  uint32_t tail4;        /* whole 4-sample pieces after the last full unit (0..3): they come through the ring too */
   uint8_t *dp;           /* next code group (channel-interleaved streams) */
   EncByteStream bytes;   /* next code bytes (mono streams) */
   EncRing<MS> ring;
@@ -346,6 +363,7 @@ __device__ __forceinline__ void enc_job_begin(EncJob<MS> &j, const EncSource<MS>
   constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
   j.sum = 0.0;
   j.units = 0;
+  j.tail4 = 0;
   if (!j.emit && j.n < AADF_TAPS) j.run = false;
   j.dp = j.blk + C * AADF_CHANNEL_HEADER_BYTES + ch * GB;
   j.bytes.begin(j.dp);
@@ -371,8 +389,12 @@ __device__ __forceinline__ void enc_job_begin(EncJob<MS> &j, const EncSource<MS>
     aadf_put_be16(hp + 14, (uint32_t)(c.w3 >> shift) & 0xFFFFu); aadf_put_be16(hp + 16, (uint32_t)c.h3 & 0xFFFFu);
   }
   j.units = ((j.n > AADF_TAPS) ? j.n - AADF_TAPS : 0u) / kEncUnit;
-  /* the samples after the last full unit are read one by one at the end: pull their line into L1 now */
-  const uint32_t tail = j.first + AADF_TAPS + j.units * kEncUnit;
+  j.tail4 = (((j.n > AADF_TAPS) ? j.n - AADF_TAPS : 0u) % kEncUnit) / 4u;
+  /* the samples after the last whole 4-sample piece are read one by one at the end: pull their line into L1 now */
+  const uint32_t tail = j.first + AADF_TAPS + j.units * kEncUnit + 4u * j.tail4;
+  /* the whole 4-sample pieces behind the last full unit: requested now, into a slot of their own, read at the very end
+   * (they join the pass's first commit group) */
+  if (j.tail4 != 0u) j.ring.issue_pieces(kEncSlots, src, j.first + AADF_TAPS + j.units * kEncUnit, j.tail4);
   if (tail < j.first + j.n) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(src.a + tail));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(src.a + j.first + j.n - 1));
@@ -475,9 +497,8 @@ __device__ __forceinline__ void enc_job_finish(EncJob<MS> &j, const EncSource<MS
   const uint32_t cnt = j.emit ? (rest + GS - 1u) / GS * GS : rest;
   uint32_t i = j.first + AADF_TAPS + j.units * kEncUnit;
   uint32_t packed = 0, inpack = 0;
-  for (uint32_t k = 0; k < cnt; k++, i++) {
+  auto one = [&](int32_t xs) {
     int32_t q;
-    const int32_t xs = (i < limit) ? src.at(i) : 0;
     packed = (packed << BITS) | enc_sample<BITS>(c, xs, sh, q);
     enc_add_square(j.sum, q);
     if (j.emit && ++inpack == GS) {
@@ -491,7 +512,23 @@ __device__ __forceinline__ void enc_job_finish(EncJob<MS> &j, const EncSource<MS
       packed = 0;
       inpack = 0;
     }
+  };
+  uint32_t k = 0;
+  if (j.tail4 != 0u) {   /* the whole 4-sample pieces behind the last full unit (requested in enc_job_begin) */
+    EncRing<MS>::template wait<0>();
+    EncUnit<MS> cur;
+    cur.read(j.ring, kEncSlots, src);
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      if ((uint32_t)g < j.tail4) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) one(cur.get(src, 4 * g + t));
+      }
+    }
+    k = 4u * j.tail4;
+    i += k;
   }
+  for (; k < cnt; k++, i++) one((i < limit) ? src.at(i) : 0);
   if (j.emit && mono) j.bytes.end();
 }
 
