@@ -2,8 +2,9 @@
  * aad_decode_fast.cuh -- the production decoder kernels (included by aad_kernels.cu).
  *
  * One thread = one (block, channel) chain (every block header reloads the whole chain state,
- * src/aad_decoder.c:364-380).  A warp task = 32/C consecutive blocks of one stream, walked in windows of
- * 128 samples per chain:
+ * src/aad_decoder.c:364-380).  A warp task = 32/C consecutive blocks of the batch's (stream, block) sequence
+ * (aad_decode_fast: a task may end in the next stream, so short streams leave no lane idle; aad_decode_wide: blocks of
+ * one stream), walked in windows of 128 samples per chain:
  *
  *   global .aad  --16-byte coalesced loads (aligned superset, prefetched one window ahead)-->
  *   shared input rows --per-lane word reads + funnel shift (any byte alignment)--> sample chain
@@ -76,6 +77,8 @@ __device__ __forceinline__ void dec_load_tables(DecTables &t)
     const int32_t qa = (step * (2 * mag + 1)) >> (BITS - 1);
     t.q[i >> 4][i & 15] = (code >> (BITS - 1)) ? -qa : qa;
   }
+  /* dec_sample merges code bits into table addresses: the tables' own address bits there must be zero */
+  if (threadIdx.x == 0 && (((uint32_t)__cvta_generic_to_shared(t.q) & 63u) || ((uint32_t)__cvta_generic_to_shared(t.delta) & 31u))) __trap();
   if (threadIdx.x < 8) {
     const int k = threadIdx.x;
     int d = 0;
@@ -87,29 +90,60 @@ __device__ __forceinline__ void dec_load_tables(DecTables &t)
   __syncthreads();
 }
 
-struct DecChain {
+__constant__ uint32_t g_dec_four = 4u;
+
+/* ADDR = 1 (the stream-spanning kernels): the chain carries complete shared-space table addresses, see dec_sample */
+template <int ADDR>
+struct DecChainT {
   int32_t h0, h1, h2, h3;
   int32_t w0, w1, w2, w3;
   int32_t idx;    /* stepsize_index */
   uint32_t four;  /* 4, opaque to the compiler (g_dec_four) */
+  uint32_t qrow;  /* ADDR: shared-space address of DecTables::q (a multiple of 64) + 32: the addend of the row multiply-add */
+  uint32_t dtab;  /* ADDR: shared-space address of DecTables::delta (a multiple of 32) */
+  __device__ __forceinline__ void tables(const DecTables &t)
+  {
+    if (ADDR) {
+      /* through volatile moves: ptxas must keep the three in registers instead of re-deriving them (constant load,
+       * SR_CgaCtaId read: variable-latency instructions) inside the sample loop */
+      asm volatile("mov.u32 %0, %1;" : "=r"(four) : "r"(g_dec_four));
+      asm volatile("mov.u32 %0, %1;" : "=r"(qrow) : "r"((uint32_t)__cvta_generic_to_shared(t.q) + 32u));
+      asm volatile("mov.u32 %0, %1;" : "=r"(dtab) : "r"((uint32_t)__cvta_generic_to_shared(t.delta)));
+    } else {
+      four = g_dec_four;
+      qrow = dtab = 0u;
+    }
+  }
 };
-
-__constant__ uint32_t g_dec_four = 4u;
+typedef DecChainT<0> DecChain;
 
 /* src/aad_decoder.c:269-318 for the code whose least significant bit sits at bit POS of v. */
-template <int BITS, int POS>
-__device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const DecTables &t)
+template <int BITS, int POS, int ADDR>
+__device__ __forceinline__ int32_t dec_sample(DecChainT<ADDR> &c, uint32_t v, const DecTables &t)
 {
   constexpr uint32_t kMagField = ((1u << (BITS - 1)) - 1u) << 2;
   const uint32_t x = (POS >= 2) ? (v >> (POS >= 2 ? POS - 2 : 0)) : (v << (POS >= 2 ? 0 : 2 - POS));   /* code at bits 2.. */
   /* 4 * (index + 8) on the multiply pipe (the ALU pipe is the one this kernel saturates): the factor comes from
    * constant memory, so ptxas cannot turn the multiply-add into an ALU-pipe LEA */
-  uint32_t row;
-  asm("mad.lo.u32 %0, %1, %2, 32;" : "=r"(row) : "r"(c.idx), "r"(c.four));
-  uint32_t qoff;   /* (row & ~0x3C) | (x & 0x3C); bits 0-1 of row are zero */
-  asm("lop3.b32 %0, %1, %2, 0x3C, 0xD8;" : "=r"(qoff) : "r"(row), "r"(x));
-  const int32_t q = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.q) + qoff);
-  const int32_t d = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.delta) + (x & kMagField));
+  int32_t q, d;
+  if (ADDR) {
+    /* Both lookups go through complete shared-space addresses formed by instructions the sample needs anyway (the table
+     * bases ride in the multiply-add's addend and in the mask operation): LDS [R].  With generic pointers ptxas re-added
+     * the table base per lookup in these kernels (2 more instructions per sample). */
+    uint32_t row, qoff, doff;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(row) : "r"(c.idx), "r"(c.four), "r"(c.qrow));
+    asm("lop3.b32 %0, %1, %2, 0x3C, 0xD8;" : "=r"(qoff) : "r"(row), "r"(x));             /* (row & ~0x3C) | (x & 0x3C) */
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(doff) : "r"(x), "n"(kMagField), "r"(c.dtab));   /* (x & kMagField) | dtab */
+    asm("ld.shared.s32 %0, [%1];" : "=r"(q) : "r"(qoff));
+    asm("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(doff));
+  } else {
+    uint32_t row;
+    asm("mad.lo.u32 %0, %1, %2, 32;" : "=r"(row) : "r"(c.idx), "r"(c.four));
+    uint32_t qoff;   /* (row & ~0x3C) | (x & 0x3C); bits 0-1 of row are zero */
+    asm("lop3.b32 %0, %1, %2, 0x3C, 0xD8;" : "=r"(qoff) : "r"(row), "r"(x));
+    q = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.q) + qoff);
+    d = *reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(t.delta) + (x & kMagField));
+  }
   const uint32_t acc = (1u << 14) + (uint32_t)c.h0 * (uint32_t)c.w0 + (uint32_t)c.h1 * (uint32_t)c.w1 +
                        (uint32_t)c.h2 * (uint32_t)c.w2 + (uint32_t)c.h3 * (uint32_t)c.w3;
   const int32_t p = (int32_t)acc >> 15;
@@ -129,8 +163,8 @@ __device__ __forceinline__ int32_t dec_sample(DecChain &c, uint32_t v, const Dec
 __device__ __forceinline__ uint32_t dec_pack2(int32_t a, int32_t b) { return __byte_perm((uint32_t)a, (uint32_t)b, 0x5410); }
 
 /* All codes of one byte (4-bit: 2, 2-bit: 4), byte at bits [8*K, 8*K+8) of v; samples appended to o[]. */
-template <int BITS, int K>
-__device__ __forceinline__ void dec_byte(DecChain &c, uint32_t v, const DecTables &t, int32_t *o)
+template <int BITS, int K, class Chain>
+__device__ __forceinline__ void dec_byte(Chain &c, uint32_t v, const DecTables &t, int32_t *o)
 {
   if (BITS == 4) {
     o[0] = dec_sample<4, 8 * K + 4>(c, v, t);
@@ -144,7 +178,8 @@ __device__ __forceinline__ void dec_byte(DecChain &c, uint32_t v, const DecTable
 }
 
 /* the 8 codes of one 3-bit group held big-endian in the low 24 bits of g */
-__device__ __forceinline__ void dec_group3(DecChain &c, uint32_t g, const DecTables &t, int32_t *o)
+template <class Chain>
+__device__ __forceinline__ void dec_group3(Chain &c, uint32_t g, const DecTables &t, int32_t *o)
 {
   o[0] = dec_sample<3, 21>(c, g, t);
   o[1] = dec_sample<3, 18>(c, g, t);
@@ -210,13 +245,18 @@ __device__ __forceinline__ uint4 dec_fetch16(const uint8_t *q, const uint8_t *en
 __device__ __forceinline__ uint32_t dec_ms2(uint32_t m, uint32_t s, bool right) { return right ? __vsubss2(m, s) : __vaddss2(m, s); }
 
 /* ms_pairs: rows 2k / 2k+1 hold the mid / side chains of one block and go out as its left / right channel */
-__device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, uint32_t first, uint32_t rows, uint32_t n_row,
+/* lanes [a, b) as a mask (a <= b <= 32) */
+__device__ __forceinline__ uint32_t dec_lanes(uint32_t a, uint32_t b)
+{
+  return (b < 32u ? (1u << b) - 1u : 0xFFFFFFFFu) & ~(a < 32u ? (1u << a) - 1u : 0xFFFFFFFFu);
+}
+
+__device__ __forceinline__ void dec_flush_ragged(const unsigned char *out_rows, uint32_t todo, uint32_t n_row,
                                                  uint32_t produced, int16_t *grow, uint32_t out_base, uint32_t lane,
                                                  bool ms_pairs = false)
 {
-  /* rows [first, rows) that still deliver samples in this window */
-  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & (rows < 32u ? (1u << rows) - 1u : 0xFFFFFFFFu) &
-                  ~(first < 32u ? (1u << first) - 1u : 0xFFFFFFFFu);
+  /* the rows of `todo` that still deliver samples in this window */
+  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & todo;
   for (; live != 0u; live &= live - 1u) {
     const uint32_t rr = (uint32_t)__ffs((int)live) - 1u;
     const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
@@ -293,18 +333,17 @@ __device__ __forceinline__ void dec_flush_frames4(const unsigned char *srow, int
   }
 }
 
-/* the same for blocks whose chains do not all deliver a whole block (see dec_flush_ragged): rows [first, rows),
+/* the same for blocks whose chains do not all deliver a whole block (see dec_flush_ragged): the rows of `todo`,
  * CH rows per block, every row of a block with the same count */
 template <int CH>
-__device__ __noinline__ void dec_flush_ragged_frames(const unsigned char *out_rows, uint32_t first, uint32_t rows,
+__device__ __noinline__ void dec_flush_ragged_frames(const unsigned char *out_rows, uint32_t todo,
                                                         uint32_t n_row, uint32_t produced, int16_t *gframe,
                                                         uint32_t out_base, uint32_t lane, bool ms)
 {
   uint32_t heads = 0u;   /* lanes that hold channel 0 of a block */
 #pragma unroll
   for (int k = 0; k < 32; k += CH) heads |= 1u << k;
-  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & heads & (rows < 32u ? (1u << rows) - 1u : 0xFFFFFFFFu) &
-                  ~(first < 32u ? (1u << first) - 1u : 0xFFFFFFFFu);
+  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & heads & todo;
   for (; live != 0u; live &= live - 1u) {
     const uint32_t rr = (uint32_t)__ffs((int)live) - 1u;
     const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
@@ -336,12 +375,16 @@ __device__ __noinline__ void dec_flush_ragged_frames(const unsigned char *out_ro
  * BULK = 1 (mono 4-bit, where every window of a block is a whole number of 16-byte pieces at a 16-byte aligned place
  * of the PCM row): every lane hands its own shared output row to the TMA unit (cp.async.bulk shared -> global) instead
  * of the warp copying 32 rows through registers. */
-template <int BITS, int C, int IL, int BULK = 0>
+/* SPAN = 1: warp tasks are runs of consecutive blocks of the whole batch and may cross from one stream into the next
+ * (streams whose block count is far from a multiple of 32 / C would otherwise idle lanes in their last task: 14 % of
+ * them for the 110 / 165 blocks of a 10-second mono clip at 2 / 3 bits, a third for 1-second clips).  SPAN = 0: tasks
+ * are blocks of one stream; everything about the stream is warp-uniform (the launcher's choice when little is wasted). */
+template <int BITS, int C, int IL, int BULK = 0, int SPAN = 0>
 __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_decode_params p)
 {
-  static_assert(!BULK || (BITS == 4 && C == 1 && IL == 0), "bulk-store flush: mono 4-bit planar");
+  static_assert(!BULK || (BITS == 4 && C == 1 && IL == 0 && SPAN == 0), "bulk-store flush: mono 4-bit planar");
   using G = DecGeom<BITS, C>;
-  extern __shared__ __align__(16) unsigned char dec_smem[];
+  extern __shared__ __align__(128) unsigned char dec_smem[];
   DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
   dec_load_tables<BITS>(tab);
 
@@ -354,13 +397,39 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
   const uint32_t spb = p.geo.samples_per_block;
   const uint32_t bs = p.geo.block_size;
   const uint32_t nblocks = p.block_end - p.block_begin;
+  /* SPAN: a warp task = IN_ROWS consecutive blocks of the batch's (stream, block) sequence: it may begin in one stream
+   * and end in the next (or span several short ones).  `single` tasks (all rows in one stream: most of them) keep
+   * arithmetic row addresses throughout. */
   const uint32_t warps_per_stream = (nblocks + G::IN_ROWS - 1) / G::IN_ROWS;
-  const uint64_t total_warps = (uint64_t)p.num_streams * warps_per_stream;
+  const uint64_t total_warps = SPAN ? ((uint64_t)p.num_streams * nblocks + G::IN_ROWS - 1) / G::IN_ROWS
+                                    : (uint64_t)p.num_streams * warps_per_stream;
   const bool ms2 = (C == 2) && p.geo.ms != 0u;   /* mid/side stereo: left / right formed in the flush */
   /* persistent: the warps of the grid share out the warp tasks round robin (the tables are built once per CTA) */
   for (uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp; gw < total_warps; gw += (uint64_t)gridDim.x * kDecWarps) {
-    const uint64_t stream = gw / warps_per_stream;
-    const uint32_t b0 = p.block_begin + (uint32_t)(gw % warps_per_stream) * G::IN_ROWS;
+    uint64_t stream0;
+    uint32_t bo0;                                    /* row 0's block, counted from block_begin */
+    if (SPAN) {
+      const uint64_t row0 = gw * G::IN_ROWS;
+      stream0 = row0 / nblocks;
+      bo0 = (uint32_t)(row0 - stream0 * nblocks);
+    } else {
+      stream0 = gw / warps_per_stream;
+      bo0 = (uint32_t)(gw % warps_per_stream) * G::IN_ROWS;
+    }
+    const bool single = !SPAN || bo0 + G::IN_ROWS <= nblocks;
+
+    /* this lane's chain */
+    const uint32_t row = lane / C, ch = lane % C;
+    uint64_t stream = stream0;
+    uint32_t bo = bo0 + row;
+    if (!single) {
+      const uint32_t over = bo / nblocks;
+      stream += over;
+      bo -= over * nblocks;
+    }
+    const bool in_batch = !SPAN || stream < p.num_streams;    /* SPAN: the batch's last task may run past its last stream */
+    if (!in_batch) stream = p.num_streams - 1u;
+    const uint32_t b = p.block_begin + bo;
 
     const uint8_t *slot = p.aad + stream * p.aad_stride;
     const uint32_t size = p.sizes ? p.sizes[stream] : p.uniform_size;
@@ -368,57 +437,90 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     if (p.read_headers) ns = dec_header_samples(slot, size, p.uniform_samples);
     const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
 
-    /* this lane's chain */
-    const uint32_t row = lane / C, ch = lane % C;
-    const uint32_t b = b0 + row;
     const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
-    const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
+    const bool have = in_batch && b < p.block_end && (uint64_t)b * spb < ns &&
+                      blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES * C <= size;
     /* samples this chain delivers: what the output buffer still holds at the block's first sample */
     const uint32_t n_row = (have && (uint64_t)b * spb < buf) ? min(spb, buf - b * spb) : 0u;
     /* rows of p.pcm start at sample p.sample_base, p.aad at byte p.byte_base of the stream (shards of one stream) */
-    const uint64_t srel = (uint64_t)b * spb - p.sample_base, srel0 = (uint64_t)b0 * spb - p.sample_base;
-    int16_t *grow, *grow0;   /* this chain's row / row 0 of the warp (IL: first frame of the block) */
-    if (IL) {
-      grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel * C;
-      grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel0 * C;
+    const uint64_t srel = (uint64_t)b * spb - p.sample_base;
+    /* this chain's row (IL: first frame of the block) */
+    int16_t *grow = IL ? (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel * C
+                       : (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + srel;
+    /* Arithmetic-address segments of the flush: lanes [0, nfull) -- rows of stream0 from row 0 of the task that deliver
+     * whole blocks, base grow0 -- and, in a task that goes on into the next stream, lanes [seg1, seg1 + nfull1) with base
+     * grow1.  Everything else (a stream's last, partial block; rows of a third stream; absent blocks) is flushed row by
+     * row (dec_flush_ragged).  All of these are multiples of C: the channels of a block share its sample count. */
+    const uint32_t full_mask = __ballot_sync(0xFFFFFFFFu, n_row == spb);
+    const uint32_t seg1 = single ? 32u : (nblocks - bo0) * C;                     /* first lane of the next stream */
+    const uint32_t nfull = min((uint32_t)__ffs((int)~full_mask) - 1u, seg1);       /* __ffs(0) - 1 wraps to all ones */
+    const bool all_full = single && nfull >= 32u;
+    uint32_t nfull1 = 0u;
+    if (!single) nfull1 = min(min((uint32_t)__ffs((int)~(full_mask >> seg1)) - 1u, 32u - seg1), nblocks * C);
+    int16_t *grow0, *grow1;
+    if (SPAN) {
+      grow0 = (int16_t *)(uintptr_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, 0);
+      grow1 = (int16_t *)(uintptr_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, seg1 & 31u);
     } else {
-      grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + (uint64_t)ch * p.pcm_ch_stride + srel;
-      grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel0;
+      const uint64_t srel0 = (uint64_t)(p.block_begin + bo0) * spb - p.sample_base;
+      grow0 = grow1 = (int16_t *)p.pcm + stream0 * p.pcm_clip_stride + (IL ? srel0 * C : srel0);
     }
-    /* rows [0, nfull) deliver whole blocks (all 32 but in a stream's last warp task); nfull is a multiple of C
-     * because the channels of a block share its sample count */
-    const uint32_t nfull = (uint32_t)__ffs((int)~__ballot_sync(0xFFFFFFFFu, n_row == spb)) - 1u;   /* __ffs(0) - 1 wraps to all ones */
-    const bool all_full = nfull >= 32u;
+    const uint32_t ragged = ~(dec_lanes(0u, nfull) | dec_lanes(seg1, seg1 + nfull1));   /* lanes flushed row by row */
 
-    /* loader role: IN_LOADS 16-byte chunks per lane per window */
-    const uint8_t *g0 = slot + (AADF_FILE_HEADER_BYTES + (uint64_t)b0 * bs - p.byte_base);       /* first block of the warp */
+    /* loader role: IN_LOADS 16-byte chunks per lane per window, the aligned superset of every row's window.
+     * SPAN: chunks of rows whose whole block lies inside its stream's data need no bounds check (`careful` == false: no
+     * row of the task is a stream's last or absent block); otherwise each chunk is checked against the end of its own
+     * row's stream. */
+    const uint8_t *rbase = slot + (blk_off - p.byte_base);
+    const uint8_t *rend = slot + ((uint64_t)size > p.byte_base ? (uint64_t)size - p.byte_base : 0u);
+    const bool careful = !SPAN || __any_sync(0xFFFFFFFFu, !in_batch || blk_off + bs > size);
     const uint8_t *ld_ptr[G::IN_LOADS];
-    uint32_t ld_smem[G::IN_LOADS];
+    uint32_t ld_smem[G::IN_LOADS], ld_lane[G::IN_LOADS];
 #pragma unroll
     for (int m = 0; m < G::IN_LOADS; m++) {
       const uint32_t f = lane + 32u * m;
       const uint32_t rr = f / G::IN_CHUNKS, cc = f % G::IN_CHUNKS;
-      const uintptr_t grr = (uintptr_t)(g0 + (uint64_t)rr * bs);
-      ld_ptr[m] = (f < (uint32_t)(G::IN_ROWS * G::IN_CHUNKS)) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
+      const bool on = f < (uint32_t)(G::IN_ROWS * G::IN_CHUNKS);
+      ld_lane[m] = on ? rr * C : 0u;
+      uintptr_t grr;
+      bool row_in = true;
+      if (SPAN) {
+        grr = (uintptr_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)rbase, ld_lane[m]);
+        row_in = __shfl_sync(0xFFFFFFFFu, (int)in_batch, ld_lane[m]) != 0;
+      } else {   /* row 0 of the task is lane 0's; rows of one stream are bs bytes apart */
+        grr = (uintptr_t)(slot + (AADF_FILE_HEADER_BYTES + (uint64_t)(p.block_begin + bo0) * bs - p.byte_base) + (uint64_t)rr * bs);
+      }
+      ld_ptr[m] = (on && row_in) ? (const uint8_t *)((grr & ~(uintptr_t)15) + 16u * cc) : nullptr;
       ld_smem[m] = rr * G::IN_PITCH + 16u * cc;
     }
-    const uint8_t *slot_end = slot + ((uint64_t)size > p.byte_base ? (uint64_t)size - p.byte_base : 0u);
-    auto fetch = [&](int m) -> uint4 { return dec_fetch16(ld_ptr[m], slot_end); };
+    auto fetch_all = [&](uint4 (&pre)[G::IN_LOADS]) {
+      if (!careful) {
+#pragma unroll
+        for (int m = 0; m < G::IN_LOADS; m++)
+          pre[m] = (ld_ptr[m] != nullptr) ? __ldg(reinterpret_cast<const uint4 *>(ld_ptr[m])) : make_uint4(0u, 0u, 0u, 0u);
+      } else {
+#pragma unroll
+        for (int m = 0; m < G::IN_LOADS; m++) {
+          const uint8_t *end = SPAN ? (const uint8_t *)(uintptr_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)rend, ld_lane[m])
+                                    : rend;
+          pre[m] = dec_fetch16(ld_ptr[m], end);
+        }
+      }
+    };
 
     /* reader role: this lane's block row in shared memory */
-    const uint32_t a_r = (uint32_t)((uintptr_t)(g0 + (uint64_t)row * bs) & 15u);
+    const uint32_t a_r = (uint32_t)((uintptr_t)rbase & 15u);
     const unsigned char *irow = in_rows + row * G::IN_PITCH;
     unsigned char *orow = out_rows + lane * (BULK ? kDecBulkPitch : kDecOutPitch);
     auto in_u8 = [&](uint32_t pos) -> uint32_t { return irow[a_r + pos]; };
 
-    DecChain c;
+    DecChainT<SPAN> c;
     c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx = 0;
-    c.four = g_dec_four;
+    c.tables(tab);
 
     const uint32_t windows = (bs + G::TB - 1) / G::TB;
     uint4 pre[G::IN_LOADS];
-#pragma unroll
-    for (int m = 0; m < G::IN_LOADS; m++) pre[m] = fetch(m);
+    fetch_all(pre);
 
     uint32_t out_base = 0;                                   /* first output sample of this window */
     for (uint32_t w = 0; w < windows; w++) {
@@ -429,10 +531,9 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       __syncwarp();
       if (w + 1 < windows) {
 #pragma unroll
-        for (int m = 0; m < G::IN_LOADS; m++) {
+        for (int m = 0; m < G::IN_LOADS; m++)
           if (ld_ptr[m] != nullptr) ld_ptr[m] += G::TB;
-          pre[m] = fetch(m);
-        }
+        fetch_all(pre);
       }
 
       uint32_t produced = 0;      /* samples this chain wrote into its output row in this window */
@@ -567,26 +668,35 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
       __syncwarp();
 
       /* flush: row rr of the warp goes out as one coalesced run of 8-byte pieces */
+      const bool mine = lane * 4u + 4u <= min(produced, spb - out_base);   /* this lane's 4 samples of every whole-block row */
       if (IL) {
         /* WAV order: the two rows of a block leave as frames, 16 bytes (4 frames) per lane and block */
-        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+        if (mine) {
           const unsigned char *srow = out_rows + 8u * lane;
           int16_t *dst = grow0 + (uint64_t)(out_base + 4u * lane) * C;
-          const uint32_t nrows = min(nfull, 32u);
-          for (uint32_t rr = 0; rr < nrows; rr += C, dst += (uint64_t)spb * C, srow += C * kDecOutPitch)
+          for (uint32_t rr = 0; rr < nfull; rr += C, dst += (uint64_t)spb * C, srow += C * kDecOutPitch)
             dec_flush_frames4<2>(srow, dst, ms2);
+          if (nfull1 != 0u) {
+            srow = out_rows + 8u * lane + seg1 * kDecOutPitch;
+            dst = grow1 + (uint64_t)(out_base + 4u * lane) * C;
+            for (uint32_t rr = 0; rr < nfull1; rr += C, dst += (uint64_t)spb * C, srow += C * kDecOutPitch)
+              dec_flush_frames4<2>(srow, dst, ms2);
+          }
         }
-        if (!all_full) dec_flush_ragged_frames<2>(out_rows, nfull, 32u, n_row, produced, grow, out_base, lane, ms2);
+        if (!all_full) dec_flush_ragged_frames<2>(out_rows, ragged, n_row, produced, grow, out_base, lane, ms2);
       } else if (ms2) {
         /* stereo mid/side: the left / right planes are formed here, from the two rows of a block (src/aad_decoder.c:458-470) */
-        if (lane * 4u + 4u <= min(produced, spb - out_base))
-          dec_flush_ms_rows(out_rows + 8u * lane, grow0 + out_base + 4u * lane, min(nfull, 32u), p.pcm_ch_stride, spb);
-        if (!all_full) dec_flush_ragged(out_rows, nfull, 32u, n_row, produced, grow, out_base, lane, true);
+        if (mine) {
+          dec_flush_ms_rows(out_rows + 8u * lane, grow0 + out_base + 4u * lane, nfull, p.pcm_ch_stride, spb);
+          if (nfull1 != 0u)
+            dec_flush_ms_rows(out_rows + 8u * lane + seg1 * kDecOutPitch, grow1 + out_base + 4u * lane, nfull1, p.pcm_ch_stride, spb);
+        }
+        if (!all_full) dec_flush_ragged(out_rows, ragged, n_row, produced, grow, out_base, lane, true);
       } else if (all_full) {
-        /* every chain of the warp delivers a whole block: row addresses are plain arithmetic and the
+        /* every chain of the warp delivers a whole block of one stream: row addresses are plain arithmetic and the
          * count is the same for every row -- `produced` (identical in every lane), clipped where the
          * last window runs past the block; both are multiples of 4 */
-        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+        if (mine) {
           const unsigned char *srow = out_rows + 8u * lane;
           int16_t *dst = grow0 + out_base + 4u * lane;
 #pragma unroll
@@ -595,15 +705,20 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
                 *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
         }
       } else {
-        /* the leading whole-block rows with arithmetic addresses, the rest one by one */
-        if (lane * 4u + 4u <= min(produced, spb - out_base)) {
+        /* the whole-block rows of the (up to) two arithmetic segments, the rest one by one */
+        if (mine) {
           const unsigned char *srow = out_rows + 8u * lane;
           int16_t *dst = grow0 + out_base + 4u * lane;
           for (uint32_t rr = 0; rr < nfull; rr++)
             *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
                 *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+          srow += seg1 * kDecOutPitch;
+          dst = grow1 + out_base + 4u * lane;
+          for (uint32_t rr = 0; rr < nfull1; rr++)
+            *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr % C) * p.pcm_ch_stride + (uint64_t)(rr / C) * spb) =
+                *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
         }
-        dec_flush_ragged(out_rows, nfull, 32u, n_row, produced, grow, out_base, lane);
+        dec_flush_ragged(out_rows, ragged, n_row, produced, grow, out_base, lane);
       }
       out_base += produced;       /* identical in every lane */
       __syncwarp();
@@ -628,7 +743,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
 {
   constexpr uint32_t GB = (BITS == 3) ? 3 : 1;
   constexpr int kLoads = BITS + 1;          /* ceil(rows * chunks / 32) <= BITS + 1 for every C */
-  extern __shared__ __align__(16) unsigned char dec_smem[];
+  extern __shared__ __align__(128) unsigned char dec_smem[];
   DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
   dec_load_tables<BITS>(tab);
 
@@ -698,7 +813,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
 
     DecChain c;
     c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx = 0;
-    c.four = g_dec_four;
+    c.tables(tab);
 
     const uint32_t windows = (bs + TB - 1) / TB;
     const uint32_t gstride = GB * C;
@@ -801,8 +916,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
           }
         }
         if (!all_full) {
-          if (C == 8) dec_flush_ragged_frames<8>(out_rows, nfull, active, n_row, produced, grow, out_base, lane, false);
-          else dec_flush_ragged_frames<4>(out_rows, nfull, active, n_row, produced, grow, out_base, lane, false);
+          if (C == 8) dec_flush_ragged_frames<8>(out_rows, dec_lanes(nfull, active), n_row, produced, grow, out_base, lane, false);
+          else dec_flush_ragged_frames<4>(out_rows, dec_lanes(nfull, active), n_row, produced, grow, out_base, lane, false);
         }
       } else {
       if (lane * 4u + 4u <= min(produced, spb - out_base)) {
@@ -816,7 +931,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
             *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(srow);
         }
       }
-      if (!all_full) dec_flush_ragged(out_rows, nfull, active, n_row, produced, grow, out_base, lane);
+      if (!all_full) dec_flush_ragged(out_rows, dec_lanes(nfull, active), n_row, produced, grow, out_base, lane);
       }
       out_base += produced;       /* identical in every lane */
       __syncwarp();
@@ -857,17 +972,32 @@ int dec_persistent_grid(K kernel, size_t smem, uint64_t warps, unsigned *grid)
   return 0;
 }
 
-template <int BITS, int C, int IL, int BULK = 0>
-int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
+template <int BITS, int C, int IL, int BULK, int SPAN>
+int dec_fast_launch_as(const aadk_decode_params &p, cudaStream_t s)
 {
   using G = DecGeom<BITS, C>;
   const size_t smem = ((sizeof(DecTables) + 15) & ~(size_t)15) + (size_t)kDecWarps * (BULK ? G::WARP_BYTES_BULK : G::WARP_BYTES);
   const uint32_t nblocks = p.block_end - p.block_begin;
-  const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
+  const uint64_t warps = SPAN ? ((uint64_t)p.num_streams * nblocks + G::IN_ROWS - 1) / G::IN_ROWS
+                              : (uint64_t)p.num_streams * ((nblocks + G::IN_ROWS - 1) / G::IN_ROWS);
   unsigned grid = 0;
-  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C, IL, BULK>, smem, warps, &grid)) return rc;
-  aad_decode_fast<BITS, C, IL, BULK><<<grid, kDecWarps * 32, smem, s>>>(p);
+  if (int rc = dec_persistent_grid(aad_decode_fast<BITS, C, IL, BULK, SPAN>, smem, warps, &grid)) return rc;
+  aad_decode_fast<BITS, C, IL, BULK, SPAN><<<grid, kDecWarps * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
+}
+
+/* Tasks that span streams (SPAN) cost a little per task (per-lane stream bookkeeping, shuffles instead of arithmetic
+ * for the loader's row pointers: +1..3 % on batches that need none of it), so they are used where per-stream tasks
+ * would idle at least 1 lane in 16: g_dec_span = 1 (default) by shape, 0 never, 2 always (tests). */
+template <int BITS, int C, int IL, int BULK = 0>
+int dec_fast_launch_bc(const aadk_decode_params &p, cudaStream_t s)
+{
+  using G = DecGeom<BITS, C>;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint32_t per_stream = (nblocks + G::IN_ROWS - 1) / G::IN_ROWS * G::IN_ROWS;
+  const bool wasteful = p.num_streams > 1u && (uint64_t)(per_stream - nblocks) * 16u >= per_stream;
+  if (!BULK && (g_dec_span == 2 || (g_dec_span == 1 && wasteful))) return dec_fast_launch_as<BITS, C, IL, 0, 1>(p, s);
+  return dec_fast_launch_as<BITS, C, IL, BULK, 0>(p, s);
 }
 
 /* the TMA flush needs every window of every block to start at a 16-byte aligned place of its PCM row */

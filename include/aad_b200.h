@@ -52,8 +52,9 @@ uint32_t AADGpu_GetMaxChannels(void);
 /* 0 (default): fast kernels wherever the shape allows (mono / stereo: aad_decode_fast, 3..8 channels:
  * aad_decode_wide), generic kernels otherwise; 1: always the generic (any channel count / alignment)
  * kernels; 2: like 0, but mono / stereo streams are decoded by aad_decode_wide too; 4: like 0, but mono 4-bit
- * streams leave shared memory through the TMA unit (cp.async.bulk).  All bit-exact; this exists for testing and
- * measurement. */
+ * streams leave shared memory through the TMA unit (cp.async.bulk); 5 / 6: like 0, but the warp tasks of aad_decode_fast
+ * always / never run on from one stream into the next (default: where per-stream tasks would idle 1 lane in 16 or
+ * more).  All bit-exact; this exists for testing and measurement. */
 void AADGpu_SetKernelPath(int path);
 /* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */

@@ -101,6 +101,43 @@ def test_fast_and_generic_kernels_agree(product, gpu_ctx, bits, channels):
 
 
 @pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("channels,ms", [(1, False), (2, False), (2, True)])
+def test_decoder_tasks_spanning_streams(product, gpu_ctx, oracle, bits, channels, ms):
+    """aad_decode_fast's warp tasks may run on from one stream into the next (kernel path 5: always, 6: never, 0: where
+    per-stream tasks would idle lanes).  Ragged batches of short streams -- 1 .. 70 blocks, so a task holds pieces of up
+    to 32 streams, partial last blocks in the middle of a task, empty and 1-sample streams, truncated data, an output
+    buffer shorter than the stream -- decode to the same samples on every path, and those are the oracle's."""
+    _, gpu = product
+    rng = np.random.default_rng(4000 + bits * 10 + channels + int(ms))
+    for block, n_max in ((64 * channels, 900), (256, 9000), (1024, 30000)):
+        n_streams = 83
+        lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+        lens[0], lens[1], lens[2], lens[5] = n_max, 1, 4, 5
+        lens[10:20] = rng.integers(1, 60, size=10)          # many streams inside one task
+        pcm = np.zeros((n_streams, channels, n_max), dtype=np.int16)
+        for i in range(n_streams):
+            pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], channels, int(lens[i]), 90 + i)
+        aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, block, ms, 0, num_samples=lens)
+        cut = sizes.copy()
+        cut[3] = max(31, sizes[3] // 2)                      # data ends inside a block
+        cut[4] = 31                                          # nothing but the file header
+        res = {}
+        for path in (5, 6, 0):
+            gpu.lib.AADGpu_SetKernelPath(path)
+            try:
+                res[path] = (gpu.decode_batch(gpu_ctx, aad, n_max, 44100, channels, bits, block, ms, sizes=sizes),
+                             gpu.decode_batch(gpu_ctx, aad, n_max, 44100, channels, bits, block, ms, sizes=cut))
+            finally:
+                gpu.lib.AADGpu_SetKernelPath(0)
+        for i in range(n_streams):
+            _, want, _ = oracle.decode(aad[i, :sizes[i]].tobytes())
+            for path in (5, 6, 0):
+                assert np.array_equal(res[path][0][i, :, :lens[i]], want), (block, path, i, lens[i])
+        for path in (5, 0):
+            assert np.array_equal(res[path][1], res[6][1]), (block, path)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
 @pytest.mark.parametrize("channels", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_wide_decoder_agrees_with_generic_and_oracle(product, gpu_ctx, oracle, bits, channels):
     """aad_decode_wide (any channel count, staged through shared memory; mono / stereo forced onto it with

@@ -8,10 +8,11 @@ import aad_b200
 from aad_b200.capi import OK, make_param
 api, gpu = aad_b200.load()
 ctx = gpu.create(0)
+gpu.lib.AADGpu_SetKernelPath(int(os.environ.get("AAD_KERNEL_PATH", "0")))   # 5 / 6: tasks always / never span streams
 dev = torch.device("cuda:0"); s = torch.cuda.current_stream().cuda_stream
 N, n = 12500, 441000
 shapes = sys.argv[1:] or ["c1b4", "c2b4", "c1b2", "c1b3"]
-res = {"lib": os.environ.get("AAD_B200_LIBRARY", "in-tree")}
+res = {"lib": os.environ.get("AAD_B200_LIBRARY", "in-tree"), "path": os.environ.get("AAD_KERNEL_PATH", "0")}
 for shape in shapes:
     ch, bits = int(shape[1]), int(shape[3])
     Nc = N // ch
