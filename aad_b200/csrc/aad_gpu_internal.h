@@ -16,7 +16,7 @@
 
 #define AADGPU_PIPE_STREAMS 3   /* H2D, kernels, D2H */
 #define AADGPU_MAX_GROUP 16     /* devices in one AADGpuGroup */
-#define AADGPU_MAX_SLICES 32    /* block-range slices a host pipeline cuts its copies into */
+#define AADGPU_MAX_SLICES 64    /* block-range slices a host pipeline cuts its copies into */
 
 struct aadgpu_buffer {
   void *ptr;

@@ -285,6 +285,30 @@ def run_sweeps(args, torch, gpu, ctx, dev, check, total_samples, peak):
             del aad
         del pcm, out
         torch.cuda.empty_cache()
+    # short clips: 1-second mono clips are 22 blocks each, so a decoder whose warp tasks stay inside one stream idles a
+    # third of its lanes; aad_decode_fast's tasks run on into the next stream (kernel path 6 = per-stream tasks, for the A/B)
+    n1 = RATE
+    N = max(1, total_samples // n1)
+    prm = make_param(1, RATE, 4, MAX_BLOCK, False, 0)
+    b = gpu.batch(N, n1, prm)
+    pcm = torch.empty((N, 1, n1), dtype=torch.int16, device=dev)
+    out = torch.empty_like(pcm)
+    aad = torch.zeros((N, int(b.aad_stream_stride)), dtype=torch.uint8, device=dev)
+    check(gpu.lib.AADGpu_SynthBatchDevice(ctx, C.byref(b), 0, pcm.data_ptr(), stream), "synth")
+    check(gpu.lib.AADGpu_EncodeBatchDevice(ctx, C.byref(b), pcm.data_ptr(), None, aad.data_ptr(), None, stream), "encode")
+    bps = 2.0 + gpu.stream_bytes(prm, n1) / n1
+    decode = lambda: check(gpu.lib.AADGpu_DecodeBatchDevice(ctx, C.byref(b), aad.data_ptr(), None, out.data_ptr(), stream), "decode")
+    ms = _timed_kernel(torch, decode)
+    gpu.lib.AADGpu_SetKernelPath(6)
+    try:
+        ms_per_stream = _timed_kernel(torch, decode)
+    finally:
+        gpu.lib.AADGpu_SetKernelPath(0)
+    dec["b4_c1_1s_clips"] = {"kernel_ms": round(ms, 3), "msamples_s": round(N * n1 / ms / 1e3, 1),
+                             "hbm_frac": round(N * n1 * bps / (ms * 1e-3) / 1e9 / peak, 5), "clips": N,
+                             "samples_per_clip": n1, "kernel_ms_with_per_stream_tasks": round(ms_per_stream, 3)}
+    del pcm, out, aad
+    torch.cuda.empty_cache()
     return dec, enc
 
 
