@@ -58,6 +58,7 @@ static AADApiResult aadgpu_fail_drained(struct AADGpu *g, const char *what, cuda
     if (g->s_in) (void)cudaStreamSynchronize(g->s_in);
     if (g->s_run) (void)cudaStreamSynchronize(g->s_run);
     if (g->s_out) (void)cudaStreamSynchronize(g->s_out);
+    if (g->s_out2) (void)cudaStreamSynchronize(g->s_out2);
   }
   (void)cudaGetLastError();
   return aadgpu_fail(what, err);
@@ -107,6 +108,7 @@ struct AADGpu *AADGpu_Create(int device)
   cudaError_t e = cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_out2, cudaStreamNonBlocking);
   for (int i = 0; i < AADGPU_MAX_SLICES && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_run[i], cudaEventDisableTiming);
@@ -140,6 +142,7 @@ void AADGpu_Destroy(struct AADGpu *g)
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_run) cudaStreamDestroy(g->s_run);
   if (g->s_out) cudaStreamDestroy(g->s_out);
+  if (g->s_out2) cudaStreamDestroy(g->s_out2);
   pthread_mutex_destroy(&g->lock);
   free(g);
 }
@@ -820,6 +823,10 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
   d.pcm_ch_stride = pitch;
 
   const uint32_t slices = pick_slices((uint64_t)N * C * ns * 2, nblk);
+  /* the .aad rows travel on a device -> host queue of their own, beside the PCM rows (the bench batch's round trip:
+   * 307 -> 296 ms; AAD_B200_D2H_QUEUES=1 puts them back behind the PCM rows, for measurement) */
+  const char *q2 = getenv("AAD_B200_D2H_QUEUES");
+  cudaStream_t s_aad = (q2 && atoi(q2) == 1) ? gpu->s_out : gpu->s_out2;
   for (uint32_t k = 0; k < slices; k++) {
     const uint32_t b0 = (uint32_t)((uint64_t)nblk * k / slices), b1 = (uint32_t)((uint64_t)nblk * (k + 1) / slices);
     const uint32_t s0 = b0 * spb, s1 = (b1 * (uint64_t)spb < ns) ? b1 * spb : ns;
@@ -833,16 +840,18 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
       CU((cudaError_t)aadk_launch_decode(&d, gpu->s_run), "decode kernel launch");
       CU(cudaEventRecord(gpu->ev_run[k], gpu->s_run), "event");
       CU(cudaStreamWaitEvent(gpu->s_out, gpu->ev_run[k], 0), "wait");
+      if (s_aad != gpu->s_out) CU(cudaStreamWaitEvent(s_aad, gpu->ev_run[k], 0), "wait");
     }
     if (aad) {
       const size_t off = b0 ? AADF_FILE_HEADER_BYTES + (size_t)b0 * bs : 0;
       const size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
       CU(copy_rows(aad + off, batch->aad_stream_stride, d_aad + off, astride, end - off, N, cudaMemcpyDeviceToHost,
-                   gpu->s_out), "D2H aad");
+                   s_aad), "D2H aad");
     }
     CU(copy_pcm_slice(batch, C, 0, d_out, pitch, reconstructed, s0, s1, gpu->s_out), "D2H pcm");
   }
   if (copies_only) CU(cudaStreamSynchronize(gpu->s_in), "sync");
+  if (s_aad != gpu->s_out) CU(cudaStreamSynchronize(s_aad), "sync");
   CU(cudaStreamSynchronize(gpu->s_out), "sync");
   if (out_sizes)
     for (uint32_t i = 0; i < N; i++)

@@ -31,6 +31,7 @@ struct AADGpu {
   int device;
   pthread_mutex_t lock;
   cudaStream_t s_in, s_run, s_out;
+  cudaStream_t s_out2;         /* second device -> host queue (the batch round trip sends .aad and PCM side by side) */
   cudaEvent_t ev_in[AADGPU_MAX_SLICES], ev_run[AADGPU_MAX_SLICES], ev_out[AADGPU_MAX_SLICES];
   void *ring_in[3], *ring_out[3];   /* pinned bounce buffers of the drop-in paths (caller memory is pageable), lazily allocated */
   struct aadgpu_buffer pcm, aad, state, lens, sizes, lut, wav, pcm2, raw, stats;
