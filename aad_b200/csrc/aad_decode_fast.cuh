@@ -468,12 +468,16 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_fast(const aadk_dec
     const uint32_t ragged = ~(dec_lanes(0u, nfull) | dec_lanes(seg1, seg1 + nfull1));   /* lanes flushed row by row */
 
     /* loader role: IN_LOADS 16-byte chunks per lane per window, the aligned superset of every row's window.
-     * SPAN: chunks of rows whose whole block lies inside its stream's data need no bounds check (`careful` == false: no
-     * row of the task is a stream's last or absent block); otherwise each chunk is checked against the end of its own
-     * row's stream. */
+     * A task whose rows all keep their windows inside their streams' data needs no bounds check (`careful` == false: no
+     * row is one of a stream's last blocks or absent: 6 tasks in 7 of the bench batch; the checks -- 64-bit compares per
+     * chunk and window -- were 7 % of the kernel's stall samples); otherwise each chunk is checked against the end of its
+     * own row's stream. */
     const uint8_t *rbase = slot + (blk_off - p.byte_base);
     const uint8_t *rend = slot + ((uint64_t)size > p.byte_base ? (uint64_t)size - p.byte_base : 0u);
-    const bool careful = !SPAN || __any_sync(0xFFFFFFFFu, !in_batch || blk_off + bs > size);
+    /* every 16-byte chunk this row's windows will ever touch -- the last window may reach past the block's end, the
+     * aligned superset 15 bytes past that -- lies inside its stream's data */
+    const uint64_t row_span = (uint64_t)((bs + G::TB - 1) / G::TB) * G::TB + 16u;
+    const bool careful = __any_sync(0xFFFFFFFFu, !in_batch || b >= p.block_end || blk_off + row_span > size);
     const uint8_t *ld_ptr[G::IN_LOADS];
     uint32_t ld_smem[G::IN_LOADS], ld_lane[G::IN_LOADS];
 #pragma unroll
