@@ -465,12 +465,24 @@ __device__ __forceinline__ void enc_job_unit(EncJob<MS> &j, const EncSource<MS> 
   if (KIND == 1) enc_job_put_unit<BITS, MS>(j, half, mono, gstride);
 }
 
-/* the full 16-sample units [u0, units) of one job */
-template <int BITS, int MS, int KIND>
+/* the full 16-sample units [u0, units) of one job.
+ * BY2: the emitting passes of aad_encode_fast<..., PAIR = 0> take two units per turn while the step index stays clear of
+ * the tiny rows for 32 samples.  Measured, tools/enc_variants.py: 12,500 chains at 0 trials (one warp per scheduler,
+ * emitting passes only) 24.4 -> 21.2 ms; no change with 50,000 chains; but the helper-lane and pairing kernels LOSE with
+ * it (98.6 -> 104.0 ms emitting passes only, -> 118.5 ms dry passes too: the slowest warps take 19 % longer while the
+ * average takes 3 %), so nothing else uses it. */
+template <int BITS, int MS, int KIND, int BY2>
 __device__ __forceinline__ void enc_job_units(EncJob<MS> &j, const EncSource<MS> &src, uint32_t u0, bool mono,
                                               uint32_t gstride, const EncShared &sh)
 {
-  for (uint32_t u = u0; u < j.units; u++) {
+  uint32_t u = u0;
+  if (BY2 && KIND == 1) {
+    for (; u + 1u < j.units && j.c.idx8 >= kEncIdxScale * (EncQuant<BITS>::kFastIndex + 16 * EncQuant<BITS>::kMaxDrop); u += 2u) {
+      enc_job_unit<BITS, MS, KIND, 0>(j, src, u, mono, gstride, sh);
+      enc_job_unit<BITS, MS, KIND, 0>(j, src, u + 1u, mono, gstride, sh);
+    }
+  }
+  for (; u < j.units; u++) {
     if (j.c.idx8 >= kEncIdxScale * EncQuant<BITS>::kFastIndex) enc_job_unit<BITS, MS, KIND, 0>(j, src, u, mono, gstride, sh);
     else enc_job_unit<BITS, MS, KIND, 1>(j, src, u, mono, gstride, sh);   /* near silence: the index may reach the tiny rows */
   }
@@ -479,7 +491,7 @@ __device__ __forceinline__ void enc_job_units(EncJob<MS> &j, const EncSource<MS>
 /* units [u0, units) of one job, then its last samples one by one; the emitting pass rounds up
  * to whole groups with zero samples (src/aad_encoder.c:592-593).  Units u0 .. u0+kEncAhead-1
  * have been requested already. */
-template <int BITS, int MS>
+template <int BITS, int MS, int BY2 = 0>
 __device__ __forceinline__ void enc_job_finish(EncJob<MS> &j, const EncSource<MS> &src, uint32_t u0, uint32_t C,
                                                const EncShared &sh)
 {
@@ -489,8 +501,8 @@ __device__ __forceinline__ void enc_job_finish(EncJob<MS> &j, const EncSource<MS
   const bool mono = (C == 1);                      /* uniform: contiguous code bytes -> word stores */
   const uint32_t gstride = C * GB;
   EncChain &c = j.c;
-  if (j.emit) enc_job_units<BITS, MS, 1>(j, src, u0, mono, gstride, sh);
-  else enc_job_units<BITS, MS, 0>(j, src, u0, mono, gstride, sh);
+  if (j.emit) enc_job_units<BITS, MS, 1, BY2>(j, src, u0, mono, gstride, sh);
+  else enc_job_units<BITS, MS, 0, BY2>(j, src, u0, mono, gstride, sh);
   const uint32_t total = (j.n > AADF_TAPS) ? j.n - AADF_TAPS : 0u;
   const uint32_t limit = j.first + j.n;
   const uint32_t rest = total - j.units * kEncUnit;
@@ -533,7 +545,7 @@ __device__ __forceinline__ void enc_job_finish(EncJob<MS> &j, const EncSource<MS
 }
 
 /* one whole pass: begin, request the first units, run */
-template <int BITS, int MS>
+template <int BITS, int MS, int BY2 = 0>
 __device__ __forceinline__ void enc_run_job(EncJob<MS> &j, const EncSource<MS> &src, uint32_t ch, uint32_t C,
                                             const EncShared &sh)
 {
@@ -543,7 +555,7 @@ __device__ __forceinline__ void enc_run_job(EncJob<MS> &j, const EncSource<MS> &
     enc_job_request<MS>(j, src, d);
     EncRing<MS>::commit();
   }
-  enc_job_finish<BITS, MS>(j, src, 0u, C, sh);
+  enc_job_finish<BITS, MS, BY2>(j, src, 0u, C, sh);
 }
 
 /* one 16-sample unit of two DRY passes interleaved instruction by instruction (enc_run_pair) */
@@ -695,7 +707,7 @@ __global__ void __launch_bounds__(256) aad_encode_fast(const aadk_encode_params 
       job.run = true;
       job.emit = emit;
       job.blk = out + (AADF_FILE_HEADER_BYTES + (uint64_t)b * bs - p.byte_base);   /* p.aad points at byte byte_base */
-      enc_run_job<BITS, MS>(job, src, ch, C, sh);
+      enc_run_job<BITS, MS, PAIR ? 0 : 1>(job, src, ch, C, sh);
       if (emit) {
         S = job.c.state();
       } else {
