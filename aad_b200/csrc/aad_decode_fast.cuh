@@ -943,6 +943,225 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_wide(const aadk_dec
   }
 }
 
+/*
+ * aad_decode_tma<BITS> -- A/B variant of aad_decode_fast<BITS, 1> (mono 4-bit / 2-bit, planar output, tasks inside one
+ * stream) whose input staging is done by the TMA unit: the batch's blocks are described to it as a 3-D tensor
+ * [stream][block][byte of the block] (CUtensorMap built per launch, dec_tma_launch), and one elected lane per warp
+ * asks for the window of all 32 block rows of its task with ONE cp.async.bulk.tensor (UTMALDG in the SASS) that
+ * completes on an mbarrier; two windows are in flight per warp (two shared buffers).  It replaces the register
+ * prefetch (IN_LOADS 16-byte loads per lane and window held in registers), the shared stores and the per-chunk
+ * pointer bookkeeping of aad_decode_fast.  The box is [32 rows][TB bytes] with the TMA's 64-byte (32-byte for 2-bit)
+ * swizzle, which spreads the 32 rows' words over 8 banks exactly like aad_decode_fast's odd row pitch.
+ *
+ * TMA needs 16-byte aligned global addresses and strides: block 0 of stream 0 (p.aad + 31) 16-byte aligned, block
+ * size and stream stride multiples of 16 (dec_tma_eligible; anything else takes the default kernel).  Rows past the
+ * tensor's block extent are zero-filled by the unit; the extent counts the whole blocks inside uniform_size, and the
+ * launcher only takes this path when every block the batch can deliver is one of those.
+ * Selected by AADGpu_SetKernelPath(7) only: measured against the default kernel in profiles/r02_decoder_experiments.md.
+ */
+__device__ __forceinline__ void dec_mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dec_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dec_mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DEC_TMA_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DEC_TMA_DONE;\n"
+      "bra DEC_TMA_WAIT;\n"
+      "DEC_TMA_DONE:\n"
+      "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+/* box at (byte c0 of the block, block c1, stream c2) -> shared memory at dst, completion counted on bar */
+__device__ __forceinline__ void dec_tma_load_3d(uint32_t dst, const void *tmap, uint32_t bar, int32_t c0, int32_t c1, int32_t c2)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int BITS>
+struct DecTmaGeom {
+  static constexpr int TB = 16 * BITS;                       /* input bytes per block per window (mono) */
+  static constexpr int STAGE_BYTES = 32 * TB;                 /* one box: 32 block rows */
+  static constexpr int SWZ_SHIFT = (TB == 64) ? 1 : 2;        /* 64-byte swizzle: address bits 7-8 onto bits 4-5; 32-byte: bit 7 onto bit 4 */
+  static constexpr uint32_t SWZ_MASK = (TB == 64) ? 3u : 1u;
+  /* tables | (pad to 1024) | 2 stages x warps | output rows x warps | 2 mbarriers x warps */
+  static constexpr size_t SMEM = ((sizeof(DecTables) + 1023) & ~(size_t)1023) + 1024 +
+                                 (size_t)kDecWarps * (2 * STAGE_BYTES + 32 * kDecOutPitch + 16);
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_decode_params p, const __grid_constant__ CUtensorMap tmap)
+{
+  static_assert(BITS == 4 || BITS == 2, "mono 4-bit / 2-bit");
+  using G = DecGeom<BITS, 1>;
+  using T = DecTmaGeom<BITS>;
+  extern __shared__ __align__(128) unsigned char dec_smem[];
+  DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
+  dec_load_tables<BITS>(tab);
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  /* the stages sit at 1024-byte aligned shared addresses: the swizzle is a function of the address */
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(dec_smem);
+  const uint32_t stages0 = (smem0 + (uint32_t)sizeof(DecTables) + 1023u) & ~1023u;
+  unsigned char *stage_base = dec_smem + (stages0 - smem0) + (size_t)warp * (2 * T::STAGE_BYTES);
+  unsigned char *out_rows = dec_smem + (stages0 - smem0) + (size_t)kDecWarps * (2 * T::STAGE_BYTES) + (size_t)warp * (32 * kDecOutPitch);
+  const uint32_t stage_addr = stages0 + warp * (2u * T::STAGE_BYTES);
+  const uint32_t bar0 = stages0 + kDecWarps * (2u * T::STAGE_BYTES + 32u * kDecOutPitch) + warp * 16u;
+  if (lane == 0) {
+    dec_mbar_init(bar0, 1u);
+    dec_mbar_init(bar0 + 8u, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const uint32_t spb = p.geo.samples_per_block;
+  const uint32_t bs = p.geo.block_size;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint32_t warps_per_stream = (nblocks + 31u) / 32u;
+  const uint64_t total_warps = (uint64_t)p.num_streams * warps_per_stream;
+  const uint32_t windows = (bs + T::TB - 1) / T::TB;
+  const uint32_t xr = ((lane >> T::SWZ_SHIFT) & T::SWZ_MASK) << 4;   /* this lane's row: byte o of its window sits at (lane * TB + o) ^ xr */
+  unsigned char *orow = out_rows + lane * kDecOutPitch;
+  uint32_t it = 0;                                                   /* windows this warp has waited for: stage it & 1, parity (it >> 1) & 1 */
+
+  /* The warp's windows -- of all its tasks, in order -- form ONE pipeline two windows deep: the first windows of the next
+   * task are asked for while the last windows of the current one are decoded (with loads held in registers that
+   * look-ahead would cost registers; here it is two integers in lane 0). */
+  const uint64_t gw_step = (uint64_t)gridDim.x * kDecWarps;
+  uint64_t next_gw = (uint64_t)blockIdx.x * kDecWarps + warp;        /* the window to ask for next: task, */
+  uint32_t next_w = 0;                                               /* window of that task */
+  auto issue_next = [&](uint32_t st) {
+    if (lane == 0 && next_gw < total_warps) {
+      const uint64_t nstream = next_gw / warps_per_stream;
+      const uint32_t nbo0 = (uint32_t)(next_gw - nstream * warps_per_stream) * 32u;
+      dec_mbar_expect_tx(bar0 + 8u * st, T::STAGE_BYTES);
+      dec_tma_load_3d(stage_addr + st * T::STAGE_BYTES, &tmap, bar0 + 8u * st, (int32_t)(next_w * T::TB),
+                      (int32_t)(p.block_begin + nbo0), (int32_t)nstream);
+      if (++next_w == windows) {
+        next_w = 0;
+        next_gw += gw_step;
+      }
+    }
+  };
+  issue_next(0u);
+  issue_next(1u);
+
+  for (uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp; gw < total_warps; gw += gw_step) {
+    const uint64_t stream = gw / warps_per_stream;
+    const uint32_t bo0 = (uint32_t)(gw % warps_per_stream) * 32u;
+    const uint32_t b = p.block_begin + bo0 + lane;
+
+    const uint8_t *slot = p.aad + stream * p.aad_stride;
+    const uint32_t size = p.uniform_size;
+    uint32_t ns = p.uniform_samples;
+    if (p.read_headers) ns = dec_header_samples(slot, size, p.uniform_samples);
+    const uint32_t buf = p.buf_samples ? p.buf_samples : ns;
+    const uint64_t blk_off = AADF_FILE_HEADER_BYTES + (uint64_t)b * bs;
+    const bool have = b < p.block_end && (uint64_t)b * spb < ns && blk_off + (uint64_t)AADF_CHANNEL_HEADER_BYTES <= size;
+    const uint32_t n_row = (have && (uint64_t)b * spb < buf) ? min(spb, buf - b * spb) : 0u;
+    const uint64_t srel = (uint64_t)b * spb - p.sample_base;
+    int16_t *grow = (int16_t *)p.pcm + stream * p.pcm_clip_stride + srel;
+    const uint32_t full_mask = __ballot_sync(0xFFFFFFFFu, n_row == spb);
+    const uint32_t nfull = min((uint32_t)__ffs((int)~full_mask) - 1u, 32u);
+    const bool all_full = nfull >= 32u;
+    int16_t *grow0 = (int16_t *)p.pcm + stream * p.pcm_clip_stride + ((uint64_t)(p.block_begin + bo0) * spb - p.sample_base);
+    const uint32_t ragged = ~dec_lanes(0u, nfull);
+
+    DecChainT<1> c;   /* complete shared-space table addresses: with generic pointers ptxas re-adds the table base per lookup here */
+    c.h0 = c.h1 = c.h2 = c.h3 = c.w0 = c.w1 = c.w2 = c.w3 = c.idx = 0;
+    c.tables(tab);
+
+    uint32_t out_base = 0;
+    for (uint32_t w = 0; w < windows; w++, it++) {
+      const uint32_t st = it & 1u;
+      dec_mbar_wait(bar0 + 8u * st, (it >> 1) & 1u);
+      const unsigned char *irow = stage_base + st * T::STAGE_BYTES + lane * T::TB;
+      auto in_u8 = [&](uint32_t o) -> uint32_t { return irow[o ^ xr]; };
+      auto in_u32 = [&](uint32_t o) -> uint32_t { return *reinterpret_cast<const uint32_t *>(irow + (o ^ xr)); };
+
+      uint32_t produced = 0, pos = 0;
+      if (w == 0) {
+        /* block header, src/aad_decoder.c:364-380 (see aad_decode_fast) */
+        const uint32_t head = (in_u8(0) << 8) | in_u8(1);
+        c.idx = (int32_t)(int16_t)(head >> 4);
+        c.idx = max(0, min(c.idx, AADF_INDEX_MAX));
+        const uint32_t shift = head & 0xFu;
+        int32_t wv[4], hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          wv[k] = (int32_t)((uint32_t)(int32_t)(int16_t)((in_u8(2 + 4 * k) << 8) | in_u8(3 + 4 * k)) << shift);
+          hv[k] = (int32_t)(int16_t)((in_u8(4 + 4 * k) << 8) | in_u8(5 + 4 * k));
+        }
+        c.w0 = wv[0]; c.w1 = wv[1]; c.w2 = wv[2]; c.w3 = wv[3];
+        c.h0 = hv[0]; c.h1 = hv[1]; c.h2 = hv[2]; c.h3 = hv[3];
+        const int32_t first4[4] = { c.h3, c.h2, c.h1, c.h0 };   /* src/aad_decoder.c:386-391 */
+        dec_emit<4>(orow, 0, first4);
+        produced = 4;
+        pos = AADF_CHANNEL_HEADER_BYTES;
+        /* half a step brings the read position to a word boundary (the window itself is 16-byte aligned here) */
+        const uint32_t v = in_u8(pos) | (in_u8(pos + 1) << 8);
+        constexpr int PB = (BITS == 4) ? 2 : 4;
+        int32_t o[2 * PB];
+        dec_byte<BITS, 0>(c, v, tab, o);
+        dec_byte<BITS, 1>(c, v, tab, o + PB);
+        dec_emit<2 * PB>(orow, produced, o);
+        produced += 2 * PB;
+        pos += G::HALF_BYTES;
+      }
+      {
+        const uint32_t left = (spb > out_base + produced) ? spb - out_base - produced : 0u;
+        const uint32_t steps = min((uint32_t)(T::TB - pos) / G::STEP_BYTES, (left + G::SPS - 1u) / G::SPS);
+#pragma unroll 2
+        for (uint32_t s = 0; s < steps; s++) {
+          const uint32_t v = in_u32(pos);
+          pos += 4;
+          constexpr int PER_BYTE = (BITS == 4) ? 2 : 4;
+          int32_t o[G::SPS];
+          dec_byte<BITS, 0>(c, v, tab, o);
+          dec_byte<BITS, 1>(c, v, tab, o + PER_BYTE);
+          dec_byte<BITS, 2>(c, v, tab, o + 2 * PER_BYTE);
+          dec_byte<BITS, 3>(c, v, tab, o + 3 * PER_BYTE);
+          dec_emit<G::SPS>(orow, produced, o);
+          produced += G::SPS;
+        }
+      }
+      __syncwarp();   /* every lane has read its row of this stage and written its output row */
+      issue_next(st);   /* the window after next -- of this task or of the warp's next one -- into the stage just read */
+
+      /* flush: as aad_decode_fast's mono planar paths */
+      const bool mine = lane * 4u + 4u <= min(produced, spb - out_base);
+      if (all_full) {
+        if (mine) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst = grow0 + out_base + 4u * lane;
+#pragma unroll
+          for (uint32_t rr = 0; rr < 32; rr++)
+            *reinterpret_cast<uint2 *>(dst + (uint64_t)rr * spb) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+        }
+      } else {
+        if (mine) {
+          const unsigned char *srow = out_rows + 8u * lane;
+          int16_t *dst = grow0 + out_base + 4u * lane;
+          for (uint32_t rr = 0; rr < nfull; rr++)
+            *reinterpret_cast<uint2 *>(dst + (uint64_t)rr * spb) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+        }
+        dec_flush_ragged(out_rows, ragged, n_row, produced, grow, out_base, lane);
+      }
+      out_base += produced;
+      __syncwarp();
+    }
+  }
+}
+
 inline bool dec_fast_eligible(const aadk_decode_params &p)
 {
   if (p.geo.channels < 1 || p.geo.channels > 32) return false;
@@ -1026,12 +1245,61 @@ int dec_wide_launch(const aadk_decode_params &p, cudaStream_t s)
   return (int)cudaGetLastError();
 }
 
+/* aad_decode_tma: what the tensor map and the kernel's shortcuts need (everything else takes the default kernel) */
+inline bool dec_tma_eligible(const aadk_decode_params &p)
+{
+  if (g_dec_tma == 0 || p.geo.channels != 1 || (p.geo.bits != 4 && p.geo.bits != 2) || p.interleaved) return false;
+  if (p.sizes != nullptr || p.byte_base != 0 || p.uniform_samples == 0) return false;
+  if (((uintptr_t)(p.aad + AADF_FILE_HEADER_BYTES) & 15u) || (p.aad_stride % 16u) || (p.geo.block_size % 16u)) return false;
+  if (p.aad_stride >= (1ull << 40) || p.num_streams == 0) return false;
+  /* every block a stream of at most uniform_samples samples can deliver lies wholly inside uniform_size (and the slot) */
+  const uint64_t need = aadf_stream_bytes_bound(p.uniform_samples, p.geo.block_size, p.geo.samples_per_block);
+  return need <= p.uniform_size && p.uniform_size <= p.aad_stride;
+}
+
+typedef CUresult (*dec_tma_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int BITS>
+int dec_tma_launch(const aadk_decode_params &p, cudaStream_t s)
+{
+  using T = DecTmaGeom<BITS>;
+  static dec_tma_encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)(e != cudaSuccess ? e : cudaErrorNotSupported);
+    encode = (dec_tma_encode_fn)fn;
+  }
+  /* [stream][block][byte]: the whole blocks inside every stream's uniform_size bytes */
+  const uint64_t rows = (p.uniform_size - AADF_FILE_HEADER_BYTES) / p.geo.block_size;
+  const cuuint64_t dims[3] = { p.geo.block_size, rows, p.num_streams };
+  const cuuint64_t strides[2] = { p.geo.block_size, p.aad_stride };
+  const cuuint32_t box[3] = { (cuuint32_t)T::TB, 32u, 1u };
+  const cuuint32_t estr[3] = { 1u, 1u, 1u };
+  CUtensorMap tmap;
+  const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(p.aad + AADF_FILE_HEADER_BYTES), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, T::TB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  const uint32_t nblocks = p.block_end - p.block_begin;
+  const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + 31u) / 32u);
+  unsigned grid = 0;
+  if (int rc = dec_persistent_grid(aad_decode_tma<BITS>, T::SMEM, warps, &grid)) return rc;
+  aad_decode_tma<BITS><<<grid, kDecWarps * 32, T::SMEM, s>>>(p, tmap);
+  g_tma_launches++;
+  return (int)cudaGetLastError();
+}
+
 /* g_dec_wide_all (tests): 1 = mono and stereo streams also go through aad_decode_wide */
 template <int BITS>
 int dec_fast_launch(const aadk_decode_params &p, cudaStream_t s)
 {
   if (p.geo.channels > 2 || (g_dec_wide_all && !p.interleaved)) return dec_wide_launch<BITS>(p, s);
   if (p.geo.channels == 1) {   /* mono: WAV order is the plane itself */
+    if ((BITS == 4 || BITS == 2) && dec_tma_eligible(p)) return dec_tma_launch<(BITS == 3 ? 4 : BITS)>(p, s);
     if (BITS == 4 && dec_bulk_eligible(p)) return dec_fast_launch_bc<(BITS == 4 ? 4 : BITS), 1, 0, (BITS == 4 ? 1 : 0)>(p, s);
     return dec_fast_launch_bc<BITS, 1, 0>(p, s);
   }

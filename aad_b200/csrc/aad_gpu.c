@@ -39,6 +39,7 @@ AADApiResult aadgpu_fail(const char *what, cudaError_t err)
 
 const char *AADGpu_LastError(void) { return tl_error; }
 uint64_t AADGpu_KernelLaunchCount(void) { return aadk_launch_count(); }
+uint64_t AADGpu_TmaLaunchCount(void) { return aadk_tma_launch_count(); }
 void AADGpu_SetKernelPath(int path) { aadk_force_generic(path); }
 void AADGpu_SetEncoderPairing(int on) { aadk_set_encoder_schedule(on ? 1 : 0); }
 void AADGpu_SetEncoderSchedule(int mode) { aadk_set_encoder_schedule(mode); }

@@ -11,6 +11,7 @@
  * All sample arithmetic is 32-bit wrapping (unsigned multiply/add, arithmetic >> on int32),
  * matching what the reference compiles to.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,6 +34,8 @@ std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_generic{0};   /* tests: route everything through the generic kernels */
 std::atomic<int> g_dec_wide_all{0};    /* tests: mono / stereo decode through the any-channel-count staged kernel too */
 std::atomic<int> g_dec_bulk{0};        /* measurement: 1 = mono 4-bit flushes through the TMA unit (cp.async.bulk): measured slower, off */
+std::atomic<unsigned long long> g_tma_launches{0};   /* launches of aad_decode_tma (tests: the path was really taken) */
+std::atomic<int> g_dec_tma{0};         /* measurement: 1 = mono 4-bit / 2-bit staging through a tensor map (aad_decode_tma, cp.async.bulk.tensor) where the layout allows */
 std::atomic<int> g_dec_span{1};        /* aad_decode_fast's warp tasks span streams: 1 = where per-stream tasks would idle lanes, 0 = never, 2 = always */
 std::atomic<int> g_enc_schedule{1};    /* tests / measurement: the encoder's pass schedule, aad_encode_roles.cuh: enc_fast_launch */
 
@@ -652,11 +655,13 @@ inline unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned)((
 extern "C" {
 
 uint64_t aadk_launch_count(void) { return g_launches; }
+uint64_t aadk_tma_launch_count(void) { return g_tma_launches; }
 void aadk_force_generic(int on)
 {
   g_force_generic = (on == 1);
   g_dec_wide_all = (on == 2);
   g_dec_bulk = (on == 4);
+  g_dec_tma = (on == 7);
   g_dec_span = (on == 5) ? 2 : (on == 6 ? 0 : 1);
 }
 void aadk_set_encoder_schedule(int mode) { g_enc_schedule = (mode >= 0 && mode <= 4) ? mode : 1; }

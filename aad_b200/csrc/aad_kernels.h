@@ -137,6 +137,7 @@ int aadk_launch_analysis_stats(const uint8_t *data, uint32_t bits, const int16_t
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t aadk_launch_count(void);
+uint64_t aadk_tma_launch_count(void);   /* launches of aad_decode_tma (kernel path 7) */
 /* tests only: 1 = always use the generic (any-shape) kernels instead of the fast paths;
  * 2 = decode mono / stereo streams with the any-channel-count staged kernel (aad_decode_wide) too;
  * 4 = mono 4-bit decode flushes its output rows through the TMA unit (cp.async.bulk shared -> global; the A/B of

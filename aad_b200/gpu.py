@@ -29,7 +29,7 @@ class AADError(RuntimeError):
 
 class GpuApi:
     SYMBOLS = (
-        "AADGpu_DeviceCount", "AADGpu_Create", "AADGpu_Destroy", "AADGpu_LastError", "AADGpu_KernelLaunchCount",
+        "AADGpu_DeviceCount", "AADGpu_Create", "AADGpu_Destroy", "AADGpu_LastError", "AADGpu_KernelLaunchCount", "AADGpu_TmaLaunchCount",
         "AADGpu_SetMaxChannels", "AADGpu_GetMaxChannels", "AADGpu_HostAlloc", "AADGpu_HostFree", "AADGpu_BindHostThread",
         "AADGpu_StreamBytesBound", "AADGpu_StreamBytes", "AADGpu_EncodeBatchDevice", "AADGpu_DecodeBatchDevice",
         "AADGpu_EncodeBatch", "AADGpu_DecodeBatch", "AADGpu_ReconstructBatch", "AADGpu_SynthBatchDevice", "AADGpu_Deinterleave16Device",
@@ -51,6 +51,7 @@ class GpuApi:
             "AADGpu_Destroy": (None, [vp]),
             "AADGpu_LastError": (C.c_char_p, []),
             "AADGpu_KernelLaunchCount": (u64, []),
+            "AADGpu_TmaLaunchCount": (u64, []),
             "AADGpu_SetMaxChannels": (None, [u32]),
             "AADGpu_GetMaxChannels": (u32, []),
             "AADGpu_HostAlloc": (vp, [C.c_size_t]),

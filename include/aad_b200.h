@@ -47,6 +47,7 @@ struct AADGpu *AADGpu_Create(int device);                /* NULL on failure */
 void AADGpu_Destroy(struct AADGpu *gpu);
 const char *AADGpu_LastError(void);                      /* thread-local, never NULL */
 uint64_t AADGpu_KernelLaunchCount(void);                 /* kernels launched by this library so far */
+uint64_t AADGpu_TmaLaunchCount(void);                    /* of those, launches of the tensor-map staged decoder (kernel path 7) */
 void AADGpu_SetMaxChannels(uint32_t max_channels);       /* 2 = stock reference limit, 8 = default */
 uint32_t AADGpu_GetMaxChannels(void);
 /* 0 (default): fast kernels wherever the shape allows (mono / stereo: aad_decode_fast, 3..8 channels:
@@ -54,7 +55,9 @@ uint32_t AADGpu_GetMaxChannels(void);
  * kernels; 2: like 0, but mono / stereo streams are decoded by aad_decode_wide too; 4: like 0, but mono 4-bit
  * streams leave shared memory through the TMA unit (cp.async.bulk); 5 / 6: like 0, but the warp tasks of aad_decode_fast
  * always / never run on from one stream into the next (default: where per-stream tasks would idle 1 lane in 16 or
- * more).  All bit-exact; this exists for testing and measurement. */
+ * more); 7: like 0, but mono 4-bit / 2-bit streams whose blocks are 16-byte aligned in device memory (stream stride and
+ * block size multiples of 16, no per-stream size array) are staged by the TMA unit through a tensor map
+ * (aad_decode_tma, cp.async.bulk.tensor + mbarrier).  All bit-exact; this exists for testing and measurement. */
 void AADGpu_SetKernelPath(int path);
 /* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */

@@ -75,6 +75,36 @@ def test_tma_bulk_store_flush_is_bit_exact(product, gpu_ctx, oracle):
         assert np.array_equal(res[1][0][i, :, :lens[i]], want), i
 
 
+@pytest.mark.parametrize("bits", [4, 2])
+def test_tma_tensor_map_staging_is_bit_exact(product, gpu_ctx, oracle, bits):
+    """kernel path 7: mono 4-bit / 2-bit blocks staged by the TMA unit through a tensor map (aad_decode_tma): ragged
+    batch (stream lengths from the headers, last blocks partial, streams shorter than a warp task), several block
+    sizes, against the default path and the oracle; the launch counter proves the TMA kernel really ran"""
+    _, gpu = product
+    rng = np.random.default_rng(78 + bits)
+    for block, n_streams, n_max in ((1024, 70, 150000), (256, 9, 20000), (1024, 3, 500)):
+        lens = rng.integers(1, n_max + 1, size=n_streams).astype(np.uint32)
+        lens[0] = n_max
+        lens[1] = 4
+        pcm = np.zeros((n_streams, 1, n_max), dtype=np.int16)
+        for i in range(n_streams):
+            pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], 1, int(lens[i]), i)
+        aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, block, False, 0, num_samples=lens)
+        res = []
+        for path in (0, 7):
+            gpu.lib.AADGpu_SetKernelPath(path)
+            before = int(gpu.lib.AADGpu_TmaLaunchCount())
+            try:
+                res.append(gpu.decode_batch(gpu_ctx, aad, n_max, 44100, 1, bits, block, False))
+            finally:
+                gpu.lib.AADGpu_SetKernelPath(0)
+            assert (int(gpu.lib.AADGpu_TmaLaunchCount()) > before) == (path == 7), (path, block)
+        assert np.array_equal(res[0], res[1]), (bits, block)
+        for i in range(0, n_streams, 9):
+            _, want, _ = oracle.decode(aad[i, :sizes[i]].tobytes())
+            assert np.array_equal(res[1][i, :, :lens[i]], want), (bits, block, i)
+
+
 @pytest.mark.parametrize("path", [0, 1, 2])
 def test_wav_order_decode_on_every_kernel_path(product, gpu_ctx, oracle, path):
     """kernel path 1 (generic kernels) has no WAV-order flush: planes + one interleave pass, same samples"""

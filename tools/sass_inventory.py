@@ -8,7 +8,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-KEYS = ["LDGSTS", "VIADDMNMX", "VIMNMX", "VABSDIFF", "LEA", "IMAD", "PRMT", "LOP3", "SHF", "LDS", "STS", "LDG", "STG",
+KEYS = ["UTMALDG", "UBLKCP", "SYNCS", "LDGSTS", "VIADDMNMX", "VIMNMX", "VABSDIFF", "LEA", "IMAD", "PRMT", "LOP3", "SHF", "LDS", "STS", "LDG", "STG",
         "SHFL", "I2F", "DADD"]
 
 
