@@ -43,10 +43,10 @@ sys.path.insert(0, str(ROOT))
 METRIC = "encode+decode round-trip throughput (bit-exact AAD ADPCM)"
 UNIT = "Msamples/s"
 RATE, CLIP_SAMPLES, CHANNELS, BITS, MAX_BLOCK, TRIALS = 44100, 441000, 1, 4, 1024, 2
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (aad_encode_fast<4,0,1>) at the
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (aad_encode_roles<4,0,0>) at the
 # default workload, from an `ncu --set full` capture of this command kept under profiles/ -- NOT measured in
 # the run, hence reported as traffic_from_profile (roofline.traffic itself stays null).
-TRAFFIC_FROM_PROFILE = {"bytes": 23.5e9, "profile": "profiles/r01_v6_encode.md"}
+TRAFFIC_FROM_PROFILE = {"bytes": 21.07e9, "profile": "profiles/r02b_encode_roles.md"}
 LONG_STREAMS = {
     "config3": {"channels": 2, "rate": 48000, "bits": 4, "samples": 172_800_000,
                 "workload": "BASELINE configs[2]: synthetic 1-hour 48 kHz 16-bit stereo stream, 4-bit, block 1024"},
