@@ -1265,13 +1265,15 @@ template <int BITS>
 int dec_tma_launch(const aadk_decode_params &p, cudaStream_t s)
 {
   using T = DecTmaGeom<BITS>;
-  static dec_tma_encode_fn encode = nullptr;
+  static std::atomic<dec_tma_encode_fn> encode_fn{nullptr};   /* contexts on different host threads launch concurrently */
+  dec_tma_encode_fn encode = encode_fn.load();
   if (!encode) {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)(e != cudaSuccess ? e : cudaErrorNotSupported);
     encode = (dec_tma_encode_fn)fn;
+    encode_fn.store(encode);
   }
   /* [stream][block][byte]: the whole blocks inside every stream's uniform_size bytes */
   const uint64_t rows = (p.uniform_size - AADF_FILE_HEADER_BYTES) / p.geo.block_size;
