@@ -236,6 +236,7 @@ int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes)
 
 /* ---- host link probe ---------------------------------------------------------------------- */
 
+static int trace_on(void);
 static double wall_seconds(void)
 {
   struct timespec t;
@@ -888,7 +889,26 @@ AADApiResult AADGpu_CopyProbeBatch(struct AADGpu *gpu, const struct AADGpuBatch 
  */
 #define AADGPU_RING_SLOTS 3
 #define AADGPU_RING_BYTES ((size_t)16 << 20)      /* per slot and direction */
-#define AADGPU_MAX_HOST_THREADS 16
+#define AADGPU_MAX_HOST_THREADS 32
+#define AADGPU_DEFAULT_HOST_THREADS 16
+
+/* measurement knobs, read once: AAD_B200_HOST_THREADS (conversion threads, caller included; default: the CPUs, at most
+ * AADGPU_DEFAULT_HOST_THREADS) and AAD_B200_RING_MIB (size of a ring slot = of a slice; default 16, at most 64)
+ * -- tools/dropin_sweep.py */
+static long env_number(const char *name, long lo, long hi, long fallback)
+{
+  const char *v = getenv(name);
+  if (!v || !*v) return fallback;
+  char *end;
+  const long x = strtol(v, &end, 10);
+  return (*end == 0 && x >= lo && x <= hi) ? x : fallback;
+}
+static size_t ring_slice_bytes(void)
+{
+  static size_t bytes = 0;     /* benign race: every thread computes the same value */
+  if (!bytes) bytes = (size_t)env_number("AAD_B200_RING_MIB", 1, 64, (long)(AADGPU_RING_BYTES >> 20)) << 20;
+  return bytes;
+}
 
 /* a minimal fork-join pool: run fn(arg, i) for i in [0, n) on the calling thread and up to 7 helpers */
 struct host_pool {
@@ -936,6 +956,8 @@ static void host_parallel_for(uint32_t n, void (*fn)(void *, uint32_t), void *ar
   pthread_mutex_lock(&g_pool.lock);
   if (!g_pool.started) {
     long cpus = sysconf(_SC_NPROCESSORS_ONLN);
+    if (cpus > AADGPU_DEFAULT_HOST_THREADS) cpus = AADGPU_DEFAULT_HOST_THREADS;
+    cpus = env_number("AAD_B200_HOST_THREADS", 1, AADGPU_MAX_HOST_THREADS, cpus);
     int want = (int)(cpus > 1 ? cpus - 1 : 0);
     if (want > AADGPU_MAX_HOST_THREADS - 1) want = AADGPU_MAX_HOST_THREADS - 1;
     for (int t = 0; t < want; t++)
@@ -966,7 +988,15 @@ static void host_parallel_for(uint32_t n, void (*fn)(void *, uint32_t), void *ar
 }
 
 /* one conversion job: `rows` rows, samples [0, n) each, cut into pieces of kConvPiece samples */
-enum { kConvPiece = 1 << 18 };
+/* 2^16 samples = 128 KiB of int16 per piece: a 16 MiB slice is 128 pieces, every thread of the pool gets several
+ * (2^18, round 2's first choice, left threads idle at the end of every slice; AAD_B200_CONV_PIECE_LOG2 for the A/B) */
+static uint64_t conv_piece_samples(void)
+{
+  static uint64_t n = 0;
+  if (!n) n = (uint64_t)1 << env_number("AAD_B200_CONV_PIECE_LOG2", 10, 24, 16);
+  return n;
+}
+#define kConvPiece conv_piece_samples()
 struct conv_job {
   int widen;                       /* 1: ring int16 -> caller int32, 0: caller int32 -> ring int16 */
   uint32_t rows, pieces_per_row;
@@ -1017,7 +1047,15 @@ static void convert_rows(int widen, int16_t *ring, int32_t *const *wide, uint32_
 }
 
 struct copy_job { uint8_t *dst; const uint8_t *src; size_t bytes; };
-enum { kCopyPiece = 1 << 20 };
+/* the .aad bytes of a slice are a quarter of its samples: 128 KiB pieces, or only a few threads would copy (1 MiB pieces
+ * = 4 threads per 16 MiB slice; AAD_B200_COPY_PIECE_LOG2 for the A/B) */
+static size_t copy_piece_bytes(void)
+{
+  static size_t n = 0;
+  if (!n) n = (size_t)1 << env_number("AAD_B200_COPY_PIECE_LOG2", 10, 24, 17);
+  return n;
+}
+#define kCopyPiece copy_piece_bytes()
 static void copy_piece(void *arg, uint32_t i)
 {
   const struct copy_job *j = (const struct copy_job *)arg;
@@ -1033,8 +1071,8 @@ static void copy_bytes(uint8_t *dst, const uint8_t *src, size_t bytes)
 static int ring_ready(struct AADGpu *gpu)
 {
   for (int i = 0; i < AADGPU_RING_SLOTS; i++) {
-    if (!gpu->ring_in[i] && cudaMallocHost(&gpu->ring_in[i], AADGPU_RING_BYTES) != cudaSuccess) goto fail;
-    if (!gpu->ring_out[i] && cudaMallocHost(&gpu->ring_out[i], AADGPU_RING_BYTES) != cudaSuccess) goto fail;
+    if (!gpu->ring_in[i] && cudaMallocHost(&gpu->ring_in[i], ring_slice_bytes()) != cudaSuccess) goto fail;
+    if (!gpu->ring_out[i] && cudaMallocHost(&gpu->ring_out[i], ring_slice_bytes()) != cudaSuccess) goto fail;
   }
   return 1;
 fail:
@@ -1046,7 +1084,7 @@ fail:
 static uint32_t ring_slice_blocks(const struct aadf_geometry *geo)
 {
   const uint64_t per_block = (uint64_t)geo->channels * geo->samples_per_block * 2;
-  uint64_t n = AADGPU_RING_BYTES / (per_block > geo->block_size ? per_block : geo->block_size);
+  uint64_t n = ring_slice_bytes() / (per_block > geo->block_size ? per_block : geo->block_size);
   return (uint32_t)(n ? n : 1);
 }
 
@@ -1171,6 +1209,10 @@ static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const 
   const uint32_t per = ring_slice_blocks(geo);
   const uint32_t slices = (num_blocks + per - 1) / per;
   const uint32_t lag = AADGPU_RING_SLOTS - 1;
+  /* AAD_B200_TRACE: where the host thread's time goes (ring waits | staging copy | enqueue | result wait | widening) */
+  const int trace = trace_on();
+  double t_phase[5] = {0, 0, 0, 0, 0}, t_mark = trace ? wall_seconds() : 0.0;
+#define PHASE(i) do { if (trace) { const double now_ = wall_seconds(); t_phase[i] += now_ - t_mark; t_mark = now_; } } while (0)
   for (uint32_t k = 0; k < slices + lag; k++) {
     if (k < slices) {
       const uint32_t slot = k % AADGPU_RING_SLOTS;
@@ -1180,8 +1222,10 @@ static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const 
       size_t end = AADF_FILE_HEADER_BYTES + (size_t)b1 * bs;
       if (end > span) end = (size_t)span;
       if (k >= AADGPU_RING_SLOTS) CU(cudaEventSynchronize(gpu->ev_in[slot]), "ring wait");
+      PHASE(0);
       if (end > off) {
         copy_bytes((uint8_t *)gpu->ring_in[slot], data + off, end - off);
+        PHASE(1);
         CU(cudaMemcpyAsync(d_aad + off, gpu->ring_in[slot], end - off, cudaMemcpyHostToDevice, gpu->s_in), "H2D aad");
       }
       CU(cudaEventRecord(gpu->ev_in[slot], gpu->s_in), "event");
@@ -1195,15 +1239,22 @@ static AADApiResult aadgpu_decode_stream_i32_unlocked(struct AADGpu *gpu, const 
         CU(cudaMemcpyAsync((int16_t *)gpu->ring_out[slot] + (uint64_t)c * (s1 - s0), d_pcm + c * pitch + s0, (size_t)(s1 - s0) * 2,
                            cudaMemcpyDeviceToHost, gpu->s_out), "D2H pcm");
       CU(cudaEventRecord(gpu->ev_out[slot], gpu->s_out), "event");
+      PHASE(2);
     }
     if (k >= lag) {
       const uint32_t j = k - lag, slot = j % AADGPU_RING_SLOTS;
       const uint32_t b0 = j * per, b1 = (b0 + per < num_blocks) ? b0 + per : num_blocks;
       const uint64_t s0 = (uint64_t)b0 * spb, s1 = ((uint64_t)b1 * spb < total) ? (uint64_t)b1 * spb : total;
       CU(cudaEventSynchronize(gpu->ev_out[slot]), "ring wait");
+      PHASE(3);
       if (s1 > s0) convert_rows(1, (int16_t *)gpu->ring_out[slot], buffer, C, s0, s1 - s0);
+      PHASE(4);
     }
   }
+#undef PHASE
+  if (trace)
+    fprintf(stderr, "[aad_b200] drop-in decode: %u slices of %u blocks: ring wait %.2f ms, staging copy %.2f, enqueue %.2f, result wait %.2f, "
+            "widening %.2f\n", slices, per, 1e3 * t_phase[0], 1e3 * t_phase[1], 1e3 * t_phase[2], 1e3 * t_phase[3], 1e3 * t_phase[4]);
   return AAD_APIRESULT_OK;
 }
 
