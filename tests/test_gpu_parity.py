@@ -229,6 +229,29 @@ def test_dropin_api_matches_compiled_reference(product, gpu_ctx, ref):
             assert np.array_equal(dec_g, dec_r), c
 
 
+def test_dropin_and_batch_api_match_patched_reference_up_to_8_channels(product, gpu_ctx, ref8):
+    """3, 4 and 8 channels directly against the compiled reference (the reference's sources with AAD_MAX_NUM_CHANNELS at 8,
+    oracle/Makefile) instead of the oracle port: the drop-in calls, and the batch path's kernels on the same streams."""
+    api, gpu = product
+    cases = [c for c in _random_cases(120, seed=23, max_channels=8) if c["ch"] >= 3][:40]
+    assert len(cases) >= 20 and {c["ch"] for c in cases} == {3, 4, 8}
+    for c in cases:
+        pcm = aadtest.signal(c["kind"], c["ch"], c["n"], c["seed"])
+        rc_r, want = ref8.encode_whole(pcm, 48000, c["bits"], c["block"], c["ms"], c["trials"])
+        rc_g, got = api.encode_whole(pcm, 48000, c["bits"], c["block"], c["ms"], c["trials"])
+        assert rc_g == rc_r and got == want, c
+        if rc_r != OK:
+            continue
+        _, dec_r, _ = ref8.decode_whole(want)
+        _, dec_g, _ = api.decode_whole(want)
+        assert np.array_equal(dec_g, dec_r), c
+        # the batch path (fast / wide kernels) on the same stream
+        aad, sizes = gpu.encode_batch(gpu_ctx, pcm[None].astype(np.int16), 48000, c["bits"], c["block"], c["ms"], c["trials"])
+        assert aad[0, :sizes[0]].tobytes() == want, c
+        dec_b = gpu.decode_batch(gpu_ctx, aad, c["n"], 48000, c["ch"], c["bits"], c["block"], c["ms"], sizes=sizes)
+        assert np.array_equal(dec_b[0], dec_r), c
+
+
 @pytest.mark.parametrize("bits", [2, 3, 4])
 @pytest.mark.parametrize("channels,ms", [(1, False), (2, False), (2, True), (8, False)])
 def test_batch_api_matches_oracle(product, gpu_ctx, oracle, bits, channels, ms):
