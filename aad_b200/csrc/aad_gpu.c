@@ -1006,6 +1006,32 @@ struct conv_job {
   uint64_t first;                  /* first sample of the slice in the caller's rows */
 };
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+/* 16 samples per turn: two sign-extending 256-bit loads' worth, two streaming 32-byte stores (a quarter of the SSE2
+ * loop's instructions; chosen at run time where the CPU has AVX2).  wide + t is 32-byte aligned on entry. */
+__attribute__((target("avx2"))) static uint64_t widen_avx2(const int16_t *narrow, int32_t *wide, uint64_t t, uint64_t b)
+{
+  for (; t + 16 <= b; t += 16) {
+    const __m256i lo = _mm256_cvtepi16_epi32(_mm_loadu_si128((const __m128i *)(narrow + t)));
+    const __m256i hi = _mm256_cvtepi16_epi32(_mm_loadu_si128((const __m128i *)(narrow + t + 8)));
+    _mm256_stream_si256((__m256i *)(wide + t), lo);
+    _mm256_stream_si256((__m256i *)(wide + t + 8), hi);
+  }
+  return t;
+}
+static int have_avx2(void)
+{
+  static int have = -1;
+  if (have < 0) {
+    const char *off = getenv("AAD_B200_NO_AVX2");     /* measurement: the SSE2 loop */
+    have = (__builtin_cpu_supports("avx2") && !(off && atoi(off) > 0)) ? 1 : 0;
+  }
+  return have;
+}
+#define AADGPU_HAVE_AVX2_PATH 1
+#endif
+
 static void conv_piece(void *arg, uint32_t i)
 {
   const struct conv_job *j = (const struct conv_job *)arg;
@@ -1018,6 +1044,12 @@ static void conv_piece(void *arg, uint32_t i)
 #if defined(__SSE2__)
     /* the caller's rows are written once and not read back here: streaming stores skip the read-for-ownership,
      * a third of the memory traffic of this loop */
+#ifdef AADGPU_HAVE_AVX2_PATH
+    if (have_avx2()) {
+      for (; t < b && (((uintptr_t)(wide + t)) & 31u); t++) wide[t] = narrow[t];
+      t = widen_avx2(narrow, wide, t, b);
+    }
+#endif
     for (; t < b && (((uintptr_t)(wide + t)) & 15u); t++) wide[t] = narrow[t];
     const __m128i zero = _mm_setzero_si128();
     for (; t + 8 <= b; t += 8) {

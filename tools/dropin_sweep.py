@@ -48,9 +48,8 @@ if __name__ == "__main__":
     else:
         out = []
         K = {"threads": "AAD_B200_HOST_THREADS", "ring_mib": "AAD_B200_RING_MIB", "conv_log2": "AAD_B200_CONV_PIECE_LOG2",
-             "copy_log2": "AAD_B200_COPY_PIECE_LOG2"}
-        points = [{}, {"conv_log2": 18, "copy_log2": 20}, {}, {"conv_log2": 18, "copy_log2": 20},      # shipped vs round 2's first choice, twice
-                  {"conv_log2": 14, "copy_log2": 15}, {"threads": 8}, {"threads": 12}, {"ring_mib": 8}, {"ring_mib": 32}, {"ring_mib": 64}]
+             "copy_log2": "AAD_B200_COPY_PIECE_LOG2", "no_avx2": "AAD_B200_NO_AVX2"}
+        points = [{}, {"no_avx2": 1}, {}, {"no_avx2": 1}, {"threads": 8}, {"threads": 8, "no_avx2": 1}, {"threads": 12}]
         for pt in points:
             env = dict(os.environ)
             env["AAD_B200_TRACE"] = "1"
