@@ -3,7 +3,7 @@ registers + shared stores) against kernel path 7 (aad_decode_tma: cp.async.bulk.
 The TMA unit needs 16-byte aligned blocks, so BOTH arms run on the same aligned layout: streams at base + 1 (block 0
 at byte 32 of the allocation), stream stride rounded up to a multiple of 16.  Prints min / all times and checksums.
 python tools/dec_tma_ab.py [shape ...]   (shape = c1b4 | c1b2)"""
-import ctypes as C, sys, json
+import ctypes as C, sys, json, os
 import torch
 sys.path.insert(0, '.')
 import aad_b200
@@ -11,7 +11,7 @@ from aad_b200.capi import OK, make_param
 api, gpu = aad_b200.load()
 ctx = gpu.create(0)
 dev = torch.device("cuda:0"); s = torch.cuda.current_stream().cuda_stream
-N, n = 12500, 441000
+N, n = int(os.environ.get("AB_CLIPS", "12500")), 441000   # AB_CLIPS=1500 for ncu captures
 res = {}
 for shape in (sys.argv[1:] or ["c1b4", "c1b2"]):
     ch, bits = int(shape[1]), int(shape[3])
