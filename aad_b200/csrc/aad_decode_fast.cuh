@@ -986,23 +986,51 @@ __device__ __forceinline__ void dec_tma_load_3d(uint32_t dst, const void *tmap, 
                :: "r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int BITS>
+/* HALF = 1: the output rows hold 64 samples and are flushed twice per window (two rows per store instruction), which
+ * brings a warp's shared memory from 12.5 KB to 8.3 KB: 24 warps per SM (64 registers allow it) instead of 16. */
+template <int BITS, int HALF>
 struct DecTmaGeom {
   static constexpr int TB = 16 * BITS;                       /* input bytes per block per window (mono) */
   static constexpr int STAGE_BYTES = 32 * TB;                 /* one box: 32 block rows */
   static constexpr int SWZ_SHIFT = (TB == 64) ? 1 : 2;        /* 64-byte swizzle: address bits 7-8 onto bits 4-5; 32-byte: bit 7 onto bit 4 */
   static constexpr uint32_t SWZ_MASK = (TB == 64) ? 3u : 1u;
+  static constexpr int WARPS = HALF ? 24 : kDecWarps;
+  static constexpr int OUT_SAMPLES = HALF ? 64 : kDecWindow;  /* samples an output row holds between flushes */
+  static constexpr int OUT_PITCH = 2 * OUT_SAMPLES + 8;       /* conflict-free 8-byte shared accesses, as kDecOutPitch */
   /* tables | (pad to 1024) | 2 stages x warps | output rows x warps | 2 mbarriers x warps */
   static constexpr size_t SMEM = ((sizeof(DecTables) + 1023) & ~(size_t)1023) + 1024 +
-                                 (size_t)kDecWarps * (2 * STAGE_BYTES + 32 * kDecOutPitch + 16);
+                                 (size_t)WARPS * (2 * STAGE_BYTES + 32 * OUT_PITCH + 16);
 };
 
-template <int BITS>
-__global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_decode_params p, const __grid_constant__ CUtensorMap tmap)
+/* dec_flush_ragged for rows of any pitch (planar mono rows only) */
+template <int PITCH>
+__device__ __forceinline__ void dec_flush_ragged_pitch(const unsigned char *out_rows, uint32_t todo, uint32_t n_row, uint32_t produced,
+                                                       int16_t *grow, uint32_t out_base, uint32_t lane)
+{
+  uint32_t live = __ballot_sync(0xFFFFFFFFu, n_row > out_base) & todo;
+  for (; live != 0u; live &= live - 1u) {
+    const uint32_t rr = (uint32_t)__ffs((int)live) - 1u;
+    const uint32_t n_rr = __shfl_sync(0xFFFFFFFFu, n_row, rr);
+    const uint64_t gp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)grow, rr);
+    const uint32_t count = min(produced, n_rr - out_base);
+    int16_t *dst = reinterpret_cast<int16_t *>((uintptr_t)gp) + out_base;
+    const unsigned char *srow = out_rows + rr * PITCH;
+    const uint32_t s0 = lane * 4u;
+    if (s0 + 4u <= count) {
+      *reinterpret_cast<uint2 *>(dst + s0) = *reinterpret_cast<const uint2 *>(srow + 2u * s0);
+    } else {
+      for (uint32_t k = s0; k < count; k++) dst[k] = *reinterpret_cast<const int16_t *>(srow + 2u * k);
+    }
+  }
+}
+
+template <int BITS, int HALF>
+__global__ void __launch_bounds__(DecTmaGeom<BITS, HALF>::WARPS * 32, 1) aad_decode_tma(const aadk_decode_params p, const __grid_constant__ CUtensorMap tmap)
 {
   static_assert(BITS == 4 || BITS == 2, "mono 4-bit / 2-bit");
   using G = DecGeom<BITS, 1>;
-  using T = DecTmaGeom<BITS>;
+  using T = DecTmaGeom<BITS, HALF>;
+  constexpr int kWarps = T::WARPS;
   extern __shared__ __align__(128) unsigned char dec_smem[];
   DecTables &tab = *reinterpret_cast<DecTables *>(dec_smem);
   dec_load_tables<BITS>(tab);
@@ -1013,9 +1041,9 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_deco
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(dec_smem);
   const uint32_t stages0 = (smem0 + (uint32_t)sizeof(DecTables) + 1023u) & ~1023u;
   unsigned char *stage_base = dec_smem + (stages0 - smem0) + (size_t)warp * (2 * T::STAGE_BYTES);
-  unsigned char *out_rows = dec_smem + (stages0 - smem0) + (size_t)kDecWarps * (2 * T::STAGE_BYTES) + (size_t)warp * (32 * kDecOutPitch);
+  unsigned char *out_rows = dec_smem + (stages0 - smem0) + (size_t)kWarps * (2 * T::STAGE_BYTES) + (size_t)warp * (32 * T::OUT_PITCH);
   const uint32_t stage_addr = stages0 + warp * (2u * T::STAGE_BYTES);
-  const uint32_t bar0 = stages0 + kDecWarps * (2u * T::STAGE_BYTES + 32u * kDecOutPitch) + warp * 16u;
+  const uint32_t bar0 = stages0 + kWarps * (2u * T::STAGE_BYTES + 32u * T::OUT_PITCH) + warp * 16u;
   if (lane == 0) {
     dec_mbar_init(bar0, 1u);
     dec_mbar_init(bar0 + 8u, 1u);
@@ -1030,14 +1058,14 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_deco
   const uint64_t total_warps = (uint64_t)p.num_streams * warps_per_stream;
   const uint32_t windows = (bs + T::TB - 1) / T::TB;
   const uint32_t xr = ((lane >> T::SWZ_SHIFT) & T::SWZ_MASK) << 4;   /* this lane's row: byte o of its window sits at (lane * TB + o) ^ xr */
-  unsigned char *orow = out_rows + lane * kDecOutPitch;
+  unsigned char *orow = out_rows + lane * T::OUT_PITCH;
   uint32_t it = 0;                                                   /* windows this warp has waited for: stage it & 1, parity (it >> 1) & 1 */
 
   /* The warp's windows -- of all its tasks, in order -- form ONE pipeline two windows deep: the first windows of the next
    * task are asked for while the last windows of the current one are decoded (with loads held in registers that
    * look-ahead would cost registers; here it is two integers in lane 0). */
-  const uint64_t gw_step = (uint64_t)gridDim.x * kDecWarps;
-  uint64_t next_gw = (uint64_t)blockIdx.x * kDecWarps + warp;        /* the window to ask for next: task, */
+  const uint64_t gw_step = (uint64_t)gridDim.x * kWarps;
+  uint64_t next_gw = (uint64_t)blockIdx.x * kWarps + warp;        /* the window to ask for next: task, */
   uint32_t next_w = 0;                                               /* window of that task */
   auto issue_next = [&](uint32_t st) {
     if (lane == 0 && next_gw < total_warps) {
@@ -1055,7 +1083,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_deco
   issue_next(0u);
   issue_next(1u);
 
-  for (uint64_t gw = (uint64_t)blockIdx.x * kDecWarps + warp; gw < total_warps; gw += gw_step) {
+  for (uint64_t gw = (uint64_t)blockIdx.x * kWarps + warp; gw < total_warps; gw += gw_step) {
     const uint64_t stream = gw / warps_per_stream;
     const uint32_t bo0 = (uint32_t)(gw % warps_per_stream) * 32u;
     const uint32_t b = p.block_begin + bo0 + lane;
@@ -1117,9 +1145,13 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_deco
         produced += 2 * PB;
         pos += G::HALF_BYTES;
       }
-      {
+      /* the window's whole steps, in one go (HALF = 0) or in two (HALF = 1: the output row holds 64 samples), a flush
+       * after each */
+#pragma unroll 1
+      for (int part = 0; part < (HALF ? 2 : 1); part++) {
         const uint32_t left = (spb > out_base + produced) ? spb - out_base - produced : 0u;
-        const uint32_t steps = min((uint32_t)(T::TB - pos) / G::STEP_BYTES, (left + G::SPS - 1u) / G::SPS);
+        uint32_t steps = min((uint32_t)(T::TB - pos) / G::STEP_BYTES, (left + G::SPS - 1u) / G::SPS);
+        if (HALF) steps = min(steps, ((uint32_t)T::OUT_SAMPLES - produced) / G::SPS);
 #pragma unroll 2
         for (uint32_t s = 0; s < steps; s++) {
           const uint32_t v = in_u32(pos);
@@ -1133,34 +1165,37 @@ __global__ void __launch_bounds__(kDecWarps * 32) aad_decode_tma(const aadk_deco
           dec_emit<G::SPS>(orow, produced, o);
           produced += G::SPS;
         }
-      }
-      __syncwarp();   /* every lane has read its row of this stage and written its output row */
-      issue_next(st);   /* the window after next -- of this task or of the warp's next one -- into the stage just read */
+        __syncwarp();   /* every lane has written its output row (and, after the last part, read its row of this stage) */
+        if (part == (HALF ? 1 : 0))
+          issue_next(st);   /* the window after next -- of this task or of the warp's next one -- into the stage just read */
 
-      /* flush: as aad_decode_fast's mono planar paths */
-      const bool mine = lane * 4u + 4u <= min(produced, spb - out_base);
-      if (all_full) {
+        /* flush: as aad_decode_fast's mono planar paths; HALF: rows of 64 samples, two of them per store instruction */
+        const uint32_t count = min(produced, spb - out_base);                 /* identical in every lane, a multiple of 4 */
+        constexpr uint32_t LPR = HALF ? 16u : 32u;                            /* lanes per row */
+        const uint32_t col = (lane % LPR) * 4u, sub = lane / LPR;             /* this lane's 4 samples, its row of a pair */
+        const bool mine = col + 4u <= count;
         if (mine) {
-          const unsigned char *srow = out_rows + 8u * lane;
-          int16_t *dst = grow0 + out_base + 4u * lane;
+          const uint32_t rows_arith = all_full ? 32u : nfull;
+          const unsigned char *srow = out_rows + 2u * col + sub * T::OUT_PITCH;
+          int16_t *dst = grow0 + out_base + col + (uint64_t)sub * spb;
+          if (all_full) {
 #pragma unroll
-          for (uint32_t rr = 0; rr < 32; rr++)
-            *reinterpret_cast<uint2 *>(dst + (uint64_t)rr * spb) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
+            for (uint32_t rr = 0; rr < 32; rr += 32u / LPR)
+              *reinterpret_cast<uint2 *>(dst + (uint64_t)rr * spb) = *reinterpret_cast<const uint2 *>(srow + rr * T::OUT_PITCH);
+          } else {
+            for (uint32_t rr = sub; rr < rows_arith; rr += 32u / LPR)
+              *reinterpret_cast<uint2 *>(dst + (uint64_t)(rr - sub) * spb) = *reinterpret_cast<const uint2 *>(srow + (rr - sub) * T::OUT_PITCH);
+          }
         }
-      } else {
-        if (mine) {
-          const unsigned char *srow = out_rows + 8u * lane;
-          int16_t *dst = grow0 + out_base + 4u * lane;
-          for (uint32_t rr = 0; rr < nfull; rr++)
-            *reinterpret_cast<uint2 *>(dst + (uint64_t)rr * spb) = *reinterpret_cast<const uint2 *>(srow + rr * kDecOutPitch);
-        }
-        dec_flush_ragged(out_rows, ragged, n_row, produced, grow, out_base, lane);
+        if (!all_full) dec_flush_ragged_pitch<T::OUT_PITCH>(out_rows, ragged, n_row, count, grow, out_base, lane);
+        out_base += produced;
+        produced = 0;
+        __syncwarp();
       }
-      out_base += produced;
-      __syncwarp();
     }
   }
 }
+
 
 inline bool dec_fast_eligible(const aadk_decode_params &p)
 {
@@ -1261,10 +1296,10 @@ typedef CUresult (*dec_tma_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint
                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int BITS>
+template <int BITS, int HALF>
 int dec_tma_launch(const aadk_decode_params &p, cudaStream_t s)
 {
-  using T = DecTmaGeom<BITS>;
+  using T = DecTmaGeom<BITS, HALF>;
   static std::atomic<dec_tma_encode_fn> encode_fn{nullptr};   /* contexts on different host threads launch concurrently */
   dec_tma_encode_fn encode = encode_fn.load();
   if (!encode) {
@@ -1288,9 +1323,13 @@ int dec_tma_launch(const aadk_decode_params &p, cudaStream_t s)
   if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   const uint32_t nblocks = p.block_end - p.block_begin;
   const uint64_t warps = (uint64_t)p.num_streams * ((nblocks + 31u) / 32u);
-  unsigned grid = 0;
-  if (int rc = dec_persistent_grid(aad_decode_tma<BITS>, T::SMEM, warps, &grid)) return rc;
-  aad_decode_tma<BITS><<<grid, kDecWarps * 32, T::SMEM, s>>>(p, tmap);
+  /* one persistent CTA per SM (the shared memory of one fills it) */
+  int dev = 0, sms = 148;
+  if (int rc = device_sm_count(&dev, &sms)) return rc;
+  if (int rc = allow_dynamic_smem(aad_decode_tma<BITS, HALF>, dev, T::SMEM)) return rc;
+  const uint64_t ctas = (warps + T::WARPS - 1) / T::WARPS;
+  const unsigned grid = (unsigned)(ctas > (uint64_t)sms ? (uint64_t)sms : ctas);
+  aad_decode_tma<BITS, HALF><<<grid, T::WARPS * 32, T::SMEM, s>>>(p, tmap);
   g_tma_launches++;
   return (int)cudaGetLastError();
 }
@@ -1301,7 +1340,8 @@ int dec_fast_launch(const aadk_decode_params &p, cudaStream_t s)
 {
   if (p.geo.channels > 2 || (g_dec_wide_all && !p.interleaved)) return dec_wide_launch<BITS>(p, s);
   if (p.geo.channels == 1) {   /* mono: WAV order is the plane itself */
-    if ((BITS == 4 || BITS == 2) && dec_tma_eligible(p)) return dec_tma_launch<(BITS == 3 ? 4 : BITS)>(p, s);
+    if ((BITS == 4 || BITS == 2) && dec_tma_eligible(p))
+      return g_dec_tma == 2 ? dec_tma_launch<(BITS == 3 ? 4 : BITS), 1>(p, s) : dec_tma_launch<(BITS == 3 ? 4 : BITS), 0>(p, s);
     if (BITS == 4 && dec_bulk_eligible(p)) return dec_fast_launch_bc<(BITS == 4 ? 4 : BITS), 1, 0, (BITS == 4 ? 1 : 0)>(p, s);
     return dec_fast_launch_bc<BITS, 1, 0>(p, s);
   }

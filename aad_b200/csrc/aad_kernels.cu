@@ -661,7 +661,7 @@ void aadk_force_generic(int on)
   g_force_generic = (on == 1);
   g_dec_wide_all = (on == 2);
   g_dec_bulk = (on == 4);
-  g_dec_tma = (on == 7);
+  g_dec_tma = (on == 7) ? 1 : (on == 8 ? 2 : 0);   /* 8: 24 warps per SM, output rows flushed twice per window */
   g_dec_span = (on == 5) ? 2 : (on == 6 ? 0 : 1);
 }
 void aadk_set_encoder_schedule(int mode) { g_enc_schedule = (mode >= 0 && mode <= 4) ? mode : 1; }

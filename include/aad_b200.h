@@ -57,7 +57,8 @@ uint32_t AADGpu_GetMaxChannels(void);
  * always / never run on from one stream into the next (default: where per-stream tasks would idle 1 lane in 16 or
  * more); 7: like 0, but mono 4-bit / 2-bit streams whose blocks are 16-byte aligned in device memory (stream stride and
  * block size multiples of 16, no per-stream size array) are staged by the TMA unit through a tensor map
- * (aad_decode_tma, cp.async.bulk.tensor + mbarrier).  All bit-exact; this exists for testing and measurement. */
+ * (aad_decode_tma, cp.async.bulk.tensor + mbarrier); 8: like 7 with 24 instead of 16 warps per SM (output rows of 64
+ * samples, flushed twice per window).  All bit-exact; this exists for testing and measurement. */
 void AADGpu_SetKernelPath(int path);
 /* 1 (default): with few chains the encoder runs the two independent dry passes of a block interleaved
  * in one thread; 0: never.  Same bytes out; this exists for testing and measurement. */

@@ -77,7 +77,8 @@ def test_tma_bulk_store_flush_is_bit_exact(product, gpu_ctx, oracle):
 
 @pytest.mark.parametrize("bits", [4, 2])
 def test_tma_tensor_map_staging_is_bit_exact(product, gpu_ctx, oracle, bits):
-    """kernel path 7: mono 4-bit / 2-bit blocks staged by the TMA unit through a tensor map (aad_decode_tma): ragged
+    """kernel paths 7 / 8: mono 4-bit / 2-bit blocks staged by the TMA unit through a tensor map (aad_decode_tma; 8 = 24
+    warps per SM, output rows flushed twice per window): ragged
     batch (stream lengths from the headers, last blocks partial, streams shorter than a warp task), several block
     sizes, against the default path and the oracle; the launch counter proves the TMA kernel really ran"""
     _, gpu = product
@@ -91,15 +92,15 @@ def test_tma_tensor_map_staging_is_bit_exact(product, gpu_ctx, oracle, bits):
             pcm[i, :, :lens[i]] = aadtest.signal(aadtest.SIGNALS[i % len(aadtest.SIGNALS)], 1, int(lens[i]), i)
         aad, sizes = gpu.encode_batch(gpu_ctx, pcm, 44100, bits, block, False, 0, num_samples=lens)
         res = []
-        for path in (0, 7):
+        for path in (0, 7, 8):
             gpu.lib.AADGpu_SetKernelPath(path)
             before = int(gpu.lib.AADGpu_TmaLaunchCount())
             try:
                 res.append(gpu.decode_batch(gpu_ctx, aad, n_max, 44100, 1, bits, block, False))
             finally:
                 gpu.lib.AADGpu_SetKernelPath(0)
-            assert (int(gpu.lib.AADGpu_TmaLaunchCount()) > before) == (path == 7), (path, block)
-        assert np.array_equal(res[0], res[1]), (bits, block)
+            assert (int(gpu.lib.AADGpu_TmaLaunchCount()) > before) == (path != 0), (path, block)
+        assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2]), (bits, block)
         for i in range(0, n_streams, 9):
             _, want, _ = oracle.decode(aad[i, :sizes[i]].tobytes())
             assert np.array_equal(res[1][i, :, :lens[i]], want), (bits, block, i)

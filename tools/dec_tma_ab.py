@@ -25,7 +25,7 @@ for shape in (sys.argv[1:] or ["c1b4", "c1b2"]):
     assert gpu.lib.AADGpu_SynthBatchDevice(ctx, C.byref(b), 0, pcm.data_ptr(), s) == OK
     assert gpu.lib.AADGpu_EncodeBatchDevice(ctx, C.byref(b), pcm.data_ptr(), None, aad_ptr, None, s) == OK
     out = torch.zeros_like(pcm)
-    for path in (0, 7, 6, 0, 7, 6):   # 6 = default kernel with per-stream tasks (what aad_decode_tma's tasks are)
+    for path in (0, 7, 8, 6, 0, 7, 8, 6):   # 6 = default kernel with per-stream tasks (what aad_decode_tma's tasks are)
         gpu.lib.AADGpu_SetKernelPath(path)
         before = int(gpu.lib.AADGpu_TmaLaunchCount())
         out.zero_()
