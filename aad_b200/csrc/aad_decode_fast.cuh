@@ -91,6 +91,10 @@ __device__ __forceinline__ void dec_load_tables(DecTables &t)
 }
 
 __constant__ uint32_t g_dec_four = 4u;
+#ifndef AAD_DEC_BIASCLIP
+#define AAD_DEC_BIASCLIP 0
+#endif
+__constant__ int32_t g_dec_one = 1;   /* AAD_DEC_BIASCLIP: an opaque 1, so that x * 1 + c stays a multiply-add */
 
 /* ADDR = 1 (the stream-spanning kernels): the chain carries complete shared-space table addresses, see dec_sample */
 template <int ADDR>
@@ -147,7 +151,16 @@ __device__ __forceinline__ int32_t dec_sample(DecChainT<ADDR> &c, uint32_t v, co
   const uint32_t acc = (1u << 14) + (uint32_t)c.h0 * (uint32_t)c.w0 + (uint32_t)c.h1 * (uint32_t)c.w1 +
                        (uint32_t)c.h2 * (uint32_t)c.w2 + (uint32_t)c.h3 * (uint32_t)c.w3;
   const int32_t p = (int32_t)acc >> 15;
+#if AAD_DEC_BIASCLIP
+  /* experiment (profiles/r02_decoder_experiments.md 6): the two-sided 16-bit clip as ONE ALU-pipe instruction on biased
+   * values -- relu(min(p + q + 32768, 65535)) - 32768 -- with the two bias adds on the multiply pipe (opaque factor 1) */
+  int32_t qb, r;
+  asm("mad.lo.s32 %0, %1, %2, 32768;" : "=r"(qb) : "r"(q), "r"(g_dec_one));
+  const int32_t rb = __viaddmin_s32_relu(p, qb, 65535);
+  asm("mad.lo.s32 %0, %1, %2, -32768;" : "=r"(r) : "r"(rb), "r"(g_dec_one));
+#else
   const int32_t r = max(__viaddmin_s32(q, p, 32767), -32768);
+#endif
   c.idx = __viaddmin_s32_relu(c.idx, d, AADF_INDEX_MAX);
   c.w0 += (int32_t)((uint32_t)q * (uint32_t)c.h0 + (1u << 14)) >> 18;
   c.w1 += (int32_t)((uint32_t)q * (uint32_t)c.h1 + (1u << 14)) >> 18;
