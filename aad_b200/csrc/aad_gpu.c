@@ -237,6 +237,7 @@ int aadgpu_reserve(struct AADGpu *gpu, struct aadgpu_buffer *b, size_t bytes)
 /* ---- host link probe ---------------------------------------------------------------------- */
 
 static int trace_on(void);
+static long env_number(const char *name, long lo, long hi, long fallback);
 static double wall_seconds(void)
 {
   struct timespec t;
@@ -550,6 +551,35 @@ static uint32_t pick_slices(uint64_t pcm_bytes, uint32_t num_blocks)
   return (uint32_t)s;
 }
 
+/* First block of slice k of `slices` over `nblk` blocks (k = slices: nblk).  With `ramp` the first and the last two slices
+ * are a quarter and a half of the others: the pipeline's fill (slice 0 up the link and through both kernels before
+ * anything comes down) and drain (the last slice down the link after everything else is done) overlap with nothing, so
+ * they should be short.  AAD_B200_SLICE_RAMP=0 / 1 overrides the default for measurement. */
+static uint32_t slice_bound(uint32_t nblk, uint32_t slices, uint32_t k, int ramp)
+{
+  if (!ramp || slices < 16) return (uint32_t)((uint64_t)nblk * k / slices);
+  const uint64_t total = 4ull * slices - 10ull;          /* in quarters of a full slice */
+  uint64_t cum;
+  if (k == 0) cum = 0;
+  else if (k == 1) cum = 1;
+  else if (k <= slices - 2) cum = 3 + 4ull * (k - 2);
+  else if (k == slices - 1) cum = total - 1;
+  else cum = total;
+  uint64_t b = (uint64_t)nblk * cum / total;
+  /* no empty slices while there are at least as many blocks as slices */
+  if (nblk >= slices) {
+    if (b < k) b = k;
+    if (b > (uint64_t)nblk - (slices - k)) b = (uint64_t)nblk - (slices - k);
+  }
+  return (uint32_t)b;
+}
+static int slice_ramp_default(void)
+{
+  static int on = -1;
+  if (on < 0) on = (int)env_number("AAD_B200_SLICE_RAMP", 0, 1, 1);   /* on: 301.1 -> 296.4 ms on the bench batch, profiles/r02_host_link.md */
+  return on;
+}
+
 /* one stream (or a shard of one): pieces of ~16 MiB so that even an eighth of an hour-long file overlaps its
  * copies with its kernels, without turning a small shard into dozens of API calls (the calls of the threads of
  * one process queue up behind each other); at most AADGPU_MAX_SLICES (one event each), at most `units` */
@@ -829,8 +859,9 @@ static AADApiResult AADGpu_ReconstructBatch_unlocked(struct AADGpu *gpu, const s
    * 307 -> 296 ms; AAD_B200_D2H_QUEUES=1 puts them back behind the PCM rows, for measurement) */
   const char *q2 = getenv("AAD_B200_D2H_QUEUES");
   cudaStream_t s_aad = (q2 && atoi(q2) == 1) ? gpu->s_out : gpu->s_out2;
+  const int ramp = slice_ramp_default();
   for (uint32_t k = 0; k < slices; k++) {
-    const uint32_t b0 = (uint32_t)((uint64_t)nblk * k / slices), b1 = (uint32_t)((uint64_t)nblk * (k + 1) / slices);
+    const uint32_t b0 = slice_bound(nblk, slices, k, ramp), b1 = slice_bound(nblk, slices, k + 1, ramp);
     const uint32_t s0 = b0 * spb, s1 = (b1 * (uint64_t)spb < ns) ? b1 * spb : ns;
     CU(copy_pcm_slice(batch, C, 1, d_pcm, pitch, (int16_t *)pcm, s0, s1, gpu->s_in), "H2D pcm");
     if (!copies_only) {   /* copies_only: the same copies with nothing between them (AADGpu_CopyProbeBatch) */
