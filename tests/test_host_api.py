@@ -341,3 +341,84 @@ def test_magic_division_tables_are_exact():
         for bits in (2, 3, 4):
             fast = (((d << np.uint64(bits - 1)) * np.uint64(m)) >> np.uint64(32)) >> np.uint64(l)
             assert np.array_equal(fast, (d << np.uint64(bits - 2)) // np.uint64(s)), (s, bits)
+
+
+def test_pipeline_slice_boundaries_are_monotone_and_complete(tmp_path):
+    """aad_gpu.c: slice_bound (block-range slices of AADGpu_ReconstructBatch, short first / last slices): for every
+    (blocks >= slices) pair the boundaries start at 0, end at the block count and never go backwards -- and are strictly
+    increasing (no empty slice) with the ramp.  The function is static: its text is compiled into a small checker."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    text = (Path(__file__).resolve().parents[1] / "aad_b200" / "csrc" / "aad_gpu.c").read_text()
+    start, end = text.index("static uint32_t slice_bound("), text.index("static int slice_ramp_default(void)")
+    src = "#include <stdint.h>\n#include <stdio.h>\n" + text[start:end] + r"""
+int main(void)
+{
+  unsigned long bad = 0, checked = 0;
+  for (uint32_t slices = 1; slices <= 64; slices++)
+    for (uint32_t nblk = slices; nblk <= 3000; nblk += (nblk < 300 ? 1 : 37))
+      for (int ramp = 0; ramp < 2; ramp++) {
+        uint32_t prev = slice_bound(nblk, slices, 0, ramp);
+        if (prev != 0) bad++;
+        for (uint32_t k = 1; k <= slices; k++, checked++) {
+          const uint32_t b = slice_bound(nblk, slices, k, ramp);
+          if (b < prev || (b == prev && (ramp || slices <= nblk))) bad++;
+          prev = b;
+        }
+        if (prev != nblk) bad++;
+      }
+  printf("%lu %lu\n", checked, bad);
+  return 0;
+}
+"""
+    c_file, exe = tmp_path / "slice_bound.c", tmp_path / "slice_bound"
+    c_file.write_text(src)
+    subprocess.run(["gcc", "-O2", "-o", str(exe), str(c_file)], check=True)
+    checked, bad = map(int, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    assert checked > 1_000_000 and bad == 0
+
+
+def test_avx2_widening_loop_equals_the_scalar_one(tmp_path):
+    """aad_gpu.c: widen_avx2 (int16 ring -> the caller's int32 rows of the drop-in DecodeWhole) against a plain loop, every
+    start offset of a 32-byte aligned destination, lengths around the 16-sample stride.  Compiled from the file's own text."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    text = (Path(__file__).resolve().parents[1] / "aad_b200" / "csrc" / "aad_gpu.c").read_text()
+    start = text.index('__attribute__((target("avx2"))) static uint64_t widen_avx2')
+    end = text.index("static int have_avx2(void)")
+    src = "#include <stdint.h>\n#include <stdio.h>\n#include <stdlib.h>\n#include <immintrin.h>\n" + text[start:end] + r"""
+int main(void)
+{
+  if (!__builtin_cpu_supports("avx2")) { printf("skip\n"); return 0; }
+  enum { N = 4096 };
+  int16_t *narrow = malloc(2 * N + 64);
+  int32_t *wide = aligned_alloc(64, 4 * N + 64), *want = malloc(4 * N + 64);
+  unsigned long bad = 0, checked = 0;
+  uint32_t x = 12345;
+  for (int i = 0; i < N; i++) { x = x * 1664525u + 1013904223u; narrow[i] = (int16_t)(x >> 16); want[i] = narrow[i]; }
+  narrow[0] = -32768; narrow[1] = 32767; want[0] = -32768; want[1] = 32767;
+  for (uint64_t t0 = 0; t0 < 64; t0 += 8)               /* wide + t0 is 32-byte aligned */
+    for (uint64_t b = t0; b < t0 + 100; b++) {
+      for (int i = 0; i < N; i++) wide[i] = 0x55555555;
+      const uint64_t t = widen_avx2(narrow, wide, t0, b);
+      _mm_sfence();
+      if (t > b || t < t0 || (b - t) >= 16 || (t - t0) % 16) bad++;
+      for (uint64_t i = 0; i < N; i++, checked++)
+        if (wide[i] != ((i >= t0 && i < t) ? want[i] : 0x55555555)) bad++;
+    }
+  printf("%lu %lu\n", checked, bad);
+  return 0;
+}
+"""
+    c_file, exe = tmp_path / "widen.c", tmp_path / "widen"
+    c_file.write_text(src)
+    subprocess.run(["gcc", "-O2", "-o", str(exe), str(c_file)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    if out == ["skip"]:
+        pytest.skip("this CPU has no AVX2")
+    checked, bad = map(int, out)
+    assert checked > 1_000_000 and bad == 0
