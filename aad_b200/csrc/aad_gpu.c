@@ -919,7 +919,7 @@ AADApiResult AADGpu_CopyProbeBatch(struct AADGpu *gpu, const struct AADGpuBatch 
  * to be touched by the host anyway.  While slice k is converted, slice k+1 is on the link and slice k+2 in the kernel.
  */
 #define AADGPU_RING_SLOTS 3
-#define AADGPU_RING_BYTES ((size_t)16 << 20)      /* per slot and direction */
+#define AADGPU_RING_BYTES ((size_t)16 << 20)      /* per slot and direction (default; AAD_B200_RING_MIB) */
 #define AADGPU_MAX_HOST_THREADS 32
 #define AADGPU_DEFAULT_HOST_THREADS 16
 
@@ -941,7 +941,8 @@ static size_t ring_slice_bytes(void)
   return bytes;
 }
 
-/* a minimal fork-join pool: run fn(arg, i) for i in [0, n) on the calling thread and up to 7 helpers */
+/* a minimal fork-join pool: run fn(arg, i) for i in [0, n) on the calling thread and its helpers (AAD_B200_HOST_THREADS - 1
+ * of them, 15 by default where the machine has the CPUs) */
 struct host_pool {
   pthread_mutex_t lock;
   pthread_cond_t wake, done;
